@@ -1,0 +1,426 @@
+// engine.cu -- C ABI of the B200 hypothesis engine (include/dsac_b200.h): device memory,
+// launches and host<->device copies.  No CPU fallback: every compute entry point needs a
+// CUDA device and fails loudly otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/dsac_b200.h"
+#include "backward.cuh"
+#include "kernels.cuh"
+#include "refine.cuh"
+
+using namespace dsac;
+
+static std::string g_create_error;
+
+struct dsac_engine {
+    dsac_config cfg;
+    std::string err;
+    int64_t launches = 0;
+    uint32_t stages = DSAC_STAGE_ALL;
+    dsac_score_hook hook = nullptr;
+    void* hook_user = nullptr;
+    int sm_count = 148;
+    // inputs (device copies for the host-buffer entry point)
+    int16_t* d_coords = nullptr;
+    int32_t* d_pix = nullptr;
+    double* d_gt = nullptr;
+    // last-call input views (device), used by fetch / backward
+    const int16_t* cur_coords = nullptr;
+    const int32_t* cur_pix = nullptr;
+    int cur_pix_shared = 0;
+    const double* cur_gt = nullptr;
+    int cur_n = 0;
+    long long cur_frame0 = 0;
+    // state
+    uint16_t* d_perm = nullptr;
+    double* d_hyp_pose = nullptr;
+    float* d_hyp_P = nullptr;
+    int32_t* d_img_idx = nullptr;
+    int32_t* d_cand_idx = nullptr;
+    long long* d_stream_ncand = nullptr;
+    uint32_t* d_status = nullptr;
+    unsigned long long* d_fragile = nullptr;
+    float* d_diffmaps = nullptr;
+    double* d_scores = nullptr;
+    double* d_sf = nullptr;
+    double* d_entropy = nullptr;
+    double* d_avg = nullptr;
+    double* d_ref = nullptr;
+    int32_t* d_inlier_map = nullptr;
+    int32_t* d_steps_done = nullptr;
+    int32_t* d_n_perm = nullptr;
+    double* d_loss = nullptr;
+    double* d_rot_err = nullptr;
+    double* d_t_err = nullptr;
+    int32_t* d_correct = nullptr;
+    unsigned int* d_frame_counter = nullptr;
+    std::vector<long long> h_stream_ncand;
+    BackwardScratch bw;
+};
+
+static int fail(dsac_engine* e, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _st = (call);                                                                        \
+        if (_st != cudaSuccess)                                                                          \
+            return fail(e, DSAC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" {
+
+const char* dsac_version(void) { return "dsac_b200 0.1 (sm_100a)"; }
+
+int dsac_default_config(dsac_config* c) {
+    if (!c) return DSAC_ERR_ARG;
+    memset(c, 0, sizeof(*c));
+    c->focal = 525.0;                  // properties.cpp:55
+    c->cx = 320.0; c->cy = 240.0;      // properties.cpp:310-311 (iw 640, ih 480, xs = ys = 0)
+    c->n_hyps = 256;                   // properties.cpp:45
+    c->thr2d = 10;                     // properties.cpp:50, int-truncated at test_ransac_softam.cpp:51
+    c->inlier_count = 100;             // properties.cpp:47
+    c->ref_steps = 8;                  // properties.cpp:46
+    c->sub_sample = 0.01;              // properties.cpp:48
+    c->alpha = 0.1; c->beta = 0.5;     // engine defaults; not reference values
+    c->seed = 1305;                    // thread_rand.h:100
+    c->n_streams = 1;
+    c->stream_skip = 6400;
+    c->max_candidates = 1 << 20;
+    c->fix_q4 = 0;
+    c->grad_clamp = 0.1;               // train_score_softam.lua:13
+    c->write_diffmaps = 1;
+    c->device = 0;
+    c->max_frames = 1;
+    c->hyps_per_cta = 0;
+    return DSAC_OK;
+}
+
+const char* dsac_last_error(const dsac_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int dsac_engine_config(const dsac_engine* e, dsac_config* out) {
+    if (!e || !out) return DSAC_ERR_ARG;
+    *out = e->cfg;
+    return DSAC_OK;
+}
+
+void dsac_engine_destroy(dsac_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    void* ptrs[] = {e->d_coords, e->d_pix, e->d_gt, e->d_perm, e->d_hyp_pose, e->d_hyp_P, e->d_img_idx, e->d_cand_idx,
+                    e->d_stream_ncand, e->d_status, e->d_fragile, e->d_diffmaps, e->d_scores, e->d_sf, e->d_entropy,
+                    e->d_avg, e->d_ref, e->d_inlier_map, e->d_steps_done, e->d_n_perm, e->d_loss, e->d_rot_err,
+                    e->d_t_err, e->d_correct, e->d_frame_counter};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    backward_scratch_free(&e->bw);
+    delete e;
+}
+
+int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
+    dsac_engine* e = nullptr;
+    if (!cfg || !out) return fail(e, DSAC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->n_hyps < 1 || cfg->n_hyps > DSAC_MAX_HYPS) return fail(e, DSAC_ERR_ARG, "n_hyps out of range [1,%d]", DSAC_MAX_HYPS);
+    if (cfg->n_streams < 1 || cfg->n_streams > cfg->n_hyps) return fail(e, DSAC_ERR_ARG, "n_streams out of range [1,n_hyps]");
+    if (cfg->inlier_count < 1 || cfg->inlier_count > K4_MAX_INLIERS) return fail(e, DSAC_ERR_ARG, "inlier_count out of range [1,%d]", K4_MAX_INLIERS);
+    if (cfg->ref_steps < 0 || cfg->ref_steps > DSAC_MAX_REF_STEPS) return fail(e, DSAC_ERR_ARG, "ref_steps out of range [0,%d]", DSAC_MAX_REF_STEPS);
+    if (cfg->max_frames < 1) return fail(e, DSAC_ERR_ARG, "max_frames must be >= 1");
+    int ndev = 0;
+    cudaError_t st = cudaGetDeviceCount(&ndev);
+    if (st != cudaSuccess || ndev == 0)
+        return fail(e, DSAC_ERR_NODEVICE, "no CUDA device available (%s); the engine has no CPU path",
+                    st == cudaSuccess ? "device count 0" : cudaGetErrorString(st));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(e, DSAC_ERR_ARG, "device %d out of range (have %d)", cfg->device, ndev);
+    e = new dsac_engine();
+    e->cfg = *cfg;
+    if (e->cfg.max_candidates <= 0) e->cfg.max_candidates = 1 << 20;
+    auto bail = [&](int code) {
+        g_create_error = e->err;
+        dsac_engine_destroy(e);
+        return code;
+    };
+#define CUC(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t _s = (call);                                                                    \
+        if (_s != cudaSuccess) {                                                                    \
+            fail(e, DSAC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_s));                  \
+            return bail(DSAC_ERR_CUDA);                                                             \
+        }                                                                                           \
+    } while (0)
+    CUC(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, cfg->device));
+    e->sm_count = prop.multiProcessorCount;
+    const size_t n = (size_t)cfg->max_frames, H = (size_t)cfg->n_hyps, N = DSAC_N;
+    CUC(cudaMalloc(&e->d_coords, n * N * 3 * sizeof(int16_t)));
+    CUC(cudaMalloc(&e->d_pix, n * N * 2 * sizeof(int32_t)));
+    CUC(cudaMalloc(&e->d_gt, n * 12 * sizeof(double)));
+    CUC(cudaMalloc(&e->d_perm, (size_t)std::max(1, cfg->ref_steps) * N * sizeof(uint16_t)));
+    CUC(cudaMalloc(&e->d_hyp_pose, n * H * 6 * sizeof(double)));
+    CUC(cudaMalloc(&e->d_hyp_P, n * H * 12 * sizeof(float)));
+    CUC(cudaMalloc(&e->d_img_idx, n * H * 4 * sizeof(int32_t)));
+    CUC(cudaMalloc(&e->d_cand_idx, n * H * sizeof(int32_t)));
+    CUC(cudaMalloc(&e->d_stream_ncand, n * cfg->n_streams * sizeof(long long)));
+    CUC(cudaMalloc(&e->d_status, n * sizeof(uint32_t)));
+    CUC(cudaMalloc(&e->d_fragile, sizeof(unsigned long long)));
+    if (cfg->write_diffmaps) CUC(cudaMalloc(&e->d_diffmaps, n * H * N * sizeof(float)));
+    CUC(cudaMalloc(&e->d_scores, n * H * sizeof(double)));
+    CUC(cudaMalloc(&e->d_sf, n * H * sizeof(double)));
+    CUC(cudaMalloc(&e->d_entropy, n * sizeof(double)));
+    CUC(cudaMalloc(&e->d_avg, n * 6 * sizeof(double)));
+    CUC(cudaMalloc(&e->d_ref, n * 6 * sizeof(double)));
+    CUC(cudaMalloc(&e->d_inlier_map, n * N * sizeof(int32_t)));
+    CUC(cudaMalloc(&e->d_steps_done, n * sizeof(int32_t)));
+    CUC(cudaMalloc(&e->d_n_perm, n * sizeof(int32_t)));
+    CUC(cudaMalloc(&e->d_loss, n * sizeof(double)));
+    CUC(cudaMalloc(&e->d_rot_err, n * sizeof(double)));
+    CUC(cudaMalloc(&e->d_t_err, n * sizeof(double)));
+    CUC(cudaMalloc(&e->d_correct, n * sizeof(int32_t)));
+    CUC(cudaMalloc(&e->d_frame_counter, n * sizeof(unsigned int)));
+    CUC(cudaMemset(e->d_frame_counter, 0, n * sizeof(unsigned int)));
+    CUC(cudaMemset(e->d_fragile, 0, sizeof(unsigned long long)));
+    CUC(cudaMemset(e->d_status, 0, n * sizeof(uint32_t)));
+    CUC(cudaMemset(e->d_steps_done, 0, n * sizeof(int32_t)));
+    CUC(cudaMemset(e->d_n_perm, 0, n * sizeof(int32_t)));
+    CUC(cudaMemset(e->d_inlier_map, 0, n * N * sizeof(int32_t)));
+    CUC(cudaMemset(e->d_ref, 0, n * 6 * sizeof(double)));
+    CUC(cudaMemset(e->d_loss, 0, n * sizeof(double)));
+    CUC(cudaMemset(e->d_rot_err, 0, n * sizeof(double)));
+    CUC(cudaMemset(e->d_t_err, 0, n * sizeof(double)));
+    CUC(cudaMemset(e->d_correct, 0, n * sizeof(int32_t)));
+    // refinement permutations: std::mt19937 randG (default seed) once per frame, iota +
+    // std::shuffle per step with the continuing generator (cnn_softam.h:1104,1112-1114) --
+    // identical for every frame, so they are built once with the very same libstdc++ calls.
+    {
+        std::mt19937 randG;
+        std::vector<uint16_t> perm((size_t)std::max(1, cfg->ref_steps) * N, 0);
+        for (int s = 0; s < cfg->ref_steps; s++) {
+            std::vector<int> idx(N);
+            for (size_t i = 0; i < N; i++) idx[i] = (int)i;
+            std::shuffle(idx.begin(), idx.end(), randG);
+            for (size_t i = 0; i < N; i++) perm[(size_t)s * N + i] = (uint16_t)idx[i];
+        }
+        CUC(cudaMemcpy(e->d_perm, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    e->h_stream_ncand.resize(n * cfg->n_streams);
+#undef CUC
+    *out = e;
+    return DSAC_OK;
+}
+
+int dsac_set_stages(dsac_engine* e, uint32_t mask) {
+    if (!e) return DSAC_ERR_ARG;
+    e->stages = mask;
+    return DSAC_OK;
+}
+
+int64_t dsac_launch_count(const dsac_engine* e) { return e ? e->launches : 0; }
+
+int dsac_set_score_hook(dsac_engine* e, dsac_score_hook fn, void* user) {
+    if (!e) return DSAC_ERR_ARG;
+    if (fn && !e->cfg.write_diffmaps) return fail(e, DSAC_ERR_ARG, "a score hook needs write_diffmaps=1");
+    e->hook = fn;
+    e->hook_user = user;
+    return DSAC_OK;
+}
+
+static int pick_tile(const dsac_engine* e, int n_frames) {
+    int H = e->cfg.n_hyps, t = e->cfg.hyps_per_cta;
+    if (t <= 0) {
+        // enough CTAs to fill the chip a few times over, but no smaller than 8 hypotheses
+        t = 64;
+        while (t > 8 && (long long)n_frames * ((H + t - 1) / t) < 4ll * e->sm_count) t >>= 1;
+    }
+    t = std::max(8, std::min(t, K2_MAX_TILE));
+    t = (t + 7) & ~7;
+    return t;
+}
+
+int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* d_coords, const int32_t* d_pix,
+                        int32_t pix_shared, const double* d_gt_jp, void* stream_v) {
+    if (!e) return DSAC_ERR_ARG;
+    if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
+    if (!d_coords || !d_pix) return fail(e, DSAC_ERR_ARG, "null input");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const dsac_config& c = e->cfg;
+    CU(cudaSetDevice(c.device));
+    e->cur_coords = d_coords;
+    e->cur_pix = d_pix;
+    e->cur_pix_shared = pix_shared;
+    e->cur_gt = d_gt_jp;
+    e->cur_n = n;
+    e->cur_frame0 = frame0;
+
+    if (e->stages & DSAC_STAGE_SAMPLE) {
+        CU(cudaMemsetAsync(e->d_status, 0, (size_t)n * sizeof(uint32_t), stream));
+        SampleParams sp;
+        sp.coords = d_coords; sp.pix = d_pix; sp.pix_stride = pix_shared ? 0 : DSAC_N * 2;
+        sp.f = c.focal; sp.cx = c.cx; sp.cy = c.cy;
+        sp.H = c.n_hyps; sp.T = c.n_streams; sp.thr = c.thr2d;
+        sp.seed = c.seed; sp.skip = c.stream_skip; sp.max_candidates = c.max_candidates;
+        sp.frame0 = frame0;
+        sp.hyp_pose = e->d_hyp_pose; sp.hyp_P = e->d_hyp_P; sp.img_idx = e->d_img_idx; sp.cand_idx = e->d_cand_idx;
+        sp.stream_ncand = e->d_stream_ncand; sp.status = e->d_status; sp.n_fragile = e->d_fragile;
+        k_sample<<<dim3(c.n_streams, n), K1_THREADS, 0, stream>>>(sp);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    if (e->stages & DSAC_STAGE_SCORE) {
+        ScoreParams kp;
+        kp.coords = d_coords; kp.pix = d_pix; kp.pix_stride = pix_shared ? 0 : DSAC_N * 2;
+        kp.hyp_P = e->d_hyp_P; kp.hyp_pose = e->d_hyp_pose;
+        kp.diffmaps = e->d_diffmaps; kp.scores = e->d_scores; kp.sf = e->d_sf; kp.entropy = e->d_entropy;
+        kp.avg_pose = e->d_avg; kp.frame_counter = e->d_frame_counter;
+        kp.H = c.n_hyps;
+        kp.tile = pick_tile(e, n);
+        kp.tiles_per_frame = (c.n_hyps + kp.tile - 1) / kp.tile;
+        kp.cxf = (float)c.cx; kp.cyf = (float)c.cy;
+        kp.thr = (float)c.thr2d;
+        kp.kbeta = (float)(c.beta * 1.4426950408889634);
+        kp.alpha = c.alpha;
+        kp.external_scores = 0;
+        dim3 grid(kp.tiles_per_frame, n);
+        if (e->d_diffmaps) k_score<true><<<grid, K2_THREADS, 0, stream>>>(kp);
+        else k_score<false><<<grid, K2_THREADS, 0, stream>>>(kp);
+        e->launches++;
+        CU(cudaGetLastError());
+        if (e->hook) {
+            // score seam (lua_calls.h:284-300): external scorer on the materialised diffmaps,
+            // then only the softmax / soft-argmax tail
+            int rc = e->hook(e->d_diffmaps, n, c.n_hyps, e->d_scores, stream_v, e->hook_user);
+            if (rc != 0) return fail(e, DSAC_ERR_ARG, "score hook returned %d", rc);
+            kp.external_scores = 1;
+            kp.tiles_per_frame = 1;
+            k_score<false><<<dim3(1, n), K2_THREADS, 0, stream>>>(kp);
+            e->launches++;
+            CU(cudaGetLastError());
+        }
+    }
+    if (e->stages & DSAC_STAGE_REFINE) {
+        RefineParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.coords = d_coords; rp.pix = d_pix; rp.pix_stride = pix_shared ? 0 : DSAC_N * 2;
+        rp.perm = e->d_perm;
+        rp.f = c.focal; rp.cx = c.cx; rp.cy = c.cy;
+        rp.thr = c.thr2d; rp.inlier_count = c.inlier_count; rp.ref_steps = c.ref_steps;
+        rp.n_jobs = n;
+        rp.job_init = e->d_avg;
+        rp.out_pose = e->d_ref;
+        rp.inlier_map = e->d_inlier_map; rp.steps_done = e->d_steps_done; rp.n_perm_steps = e->d_n_perm;
+        rp.status = e->d_status;
+        if ((e->stages & DSAC_STAGE_EVAL) && d_gt_jp) {
+            rp.gt_jp = d_gt_jp;
+            rp.loss = e->d_loss; rp.rot_err = e->d_rot_err; rp.t_err = e->d_t_err; rp.correct = e->d_correct;
+        }
+        k_refine<<<n, K4_THREADS, 0, stream>>>(rp);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    return DSAC_OK;
+}
+
+int dsac_fetch(dsac_engine* e, int32_t n, dsac_forward_out* o, void* stream_v) {
+    if (!e || !o) return DSAC_ERR_ARG;
+    if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const size_t H = e->cfg.n_hyps, N = DSAC_N, T = e->cfg.n_streams, nn = (size_t)n;
+    CU(cudaSetDevice(e->cfg.device));
+#define D2H(dst, src, bytes)                                                                    \
+    do {                                                                                        \
+        if ((dst) && (src)) CU(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, stream)); \
+    } while (0)
+    D2H(o->hyp_pose, e->d_hyp_pose, nn * H * 6 * sizeof(double));
+    D2H(o->img_idx, e->d_img_idx, nn * H * 4 * sizeof(int32_t));
+    D2H(o->cand_idx, e->d_cand_idx, nn * H * sizeof(int32_t));
+    D2H(o->scores, e->d_scores, nn * H * sizeof(double));
+    D2H(o->sf, e->d_sf, nn * H * sizeof(double));
+    if (o->diffmaps) {
+        if (!e->d_diffmaps) return fail(e, DSAC_ERR_ARG, "diffmaps requested but the engine was created with write_diffmaps=0");
+        D2H(o->diffmaps, e->d_diffmaps, nn * H * N * sizeof(float));
+    }
+    D2H(o->entropy, e->d_entropy, nn * sizeof(double));
+    D2H(o->avg_pose, e->d_avg, nn * 6 * sizeof(double));
+    D2H(o->ref_pose, e->d_ref, nn * 6 * sizeof(double));
+    D2H(o->inlier_map, e->d_inlier_map, nn * N * sizeof(int32_t));
+    D2H(o->ref_steps_done, e->d_steps_done, nn * sizeof(int32_t));
+    D2H(o->n_perm_steps, e->d_n_perm, nn * sizeof(int32_t));
+    D2H(o->loss, e->d_loss, nn * sizeof(double));
+    D2H(o->rot_err, e->d_rot_err, nn * sizeof(double));
+    D2H(o->t_err, e->d_t_err, nn * sizeof(double));
+    D2H(o->correct, e->d_correct, nn * sizeof(int32_t));
+    D2H(o->status, e->d_status, nn * sizeof(uint32_t));
+    if (o->n_candidates) D2H(e->h_stream_ncand.data(), e->d_stream_ncand, nn * T * sizeof(long long));
+#undef D2H
+    CU(cudaStreamSynchronize(stream));
+    if (o->n_candidates)
+        for (size_t f = 0; f < nn; f++) {
+            long long s = 0;
+            for (size_t t = 0; t < T; t++) s += e->h_stream_ncand[f * T + t];
+            o->n_candidates[f] = s;
+        }
+    return DSAC_OK;
+}
+
+int dsac_device_view_get(dsac_engine* e, dsac_device_view* v) {
+    if (!e || !v) return DSAC_ERR_ARG;
+    v->diffmaps = e->d_diffmaps;
+    v->hyp_pose = e->d_hyp_pose;
+    v->scores = e->d_scores;
+    v->sf = e->d_sf;
+    v->avg_pose = e->d_avg;
+    v->ref_pose = e->d_ref;
+    v->img_idx = e->d_img_idx;
+    return DSAC_OK;
+}
+
+int dsac_forward(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
+                 int32_t pix_shared, const double* gt_jp, dsac_forward_out* out) {
+    if (!e) return DSAC_ERR_ARG;
+    if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
+    if (!coords || !pix) return fail(e, DSAC_ERR_ARG, "null input");
+    CU(cudaSetDevice(e->cfg.device));
+    cudaStream_t stream = 0;
+    const size_t N = DSAC_N, nn = (size_t)n;
+    CU(cudaMemcpyAsync(e->d_coords, coords, nn * N * 3 * sizeof(int16_t), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(e->d_pix, pix, (pix_shared ? 1 : nn) * N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    if (gt_jp) CU(cudaMemcpyAsync(e->d_gt, gt_jp, nn * 12 * sizeof(double), cudaMemcpyHostToDevice, stream));
+    int rc = dsac_forward_device(e, n, frame0, e->d_coords, e->d_pix, pix_shared, gt_jp ? e->d_gt : nullptr, stream);
+    if (rc != DSAC_OK) return rc;
+    if (out) return dsac_fetch(e, n, out, stream);
+    CU(cudaStreamSynchronize(stream));
+    return DSAC_OK;
+}
+
+int dsac_backward(dsac_engine* e, int32_t n, const int16_t* coords, const int32_t* pix, int32_t pix_shared,
+                  const double* gt_jp, dsac_backward_out* out) {
+    if (!e || !out) return DSAC_ERR_ARG;
+    return backward_run(e, n, coords, pix, pix_shared, gt_jp, out);
+}
+
+int dsac_kabsch(dsac_engine* e, int32_t n, int32_t m, const double* a, const double* b, double* R, double* t) {
+    if (!e) return DSAC_ERR_ARG;
+    return kabsch_run(e, n, m, a, b, R, t);
+}
+
+}  // extern "C"
+
+#include "backward_host.inc"

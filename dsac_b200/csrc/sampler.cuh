@@ -1,0 +1,100 @@
+// sampler.cuh -- the minimal-set sampler's random stream, reproduced on the device.
+//
+// The reference draws every minimal set from a per-OpenMP-thread std::mt19937
+// (thread_rand.cpp:40-69) through fresh std::uniform_int_distribution<int>(0,39) objects
+// (irand, thread_rand.cpp:95-98; call sites cnn_softam.h:1024-1025), re-drawing a cell
+// that was already chosen (cnn_softam.h:1027-1031).  "Bit-exact sampled indices" therefore
+// means reproducing (a) the MT19937 output sequence and (b) libstdc++ 13's Lemire
+// down-scaling (bits/uniform_int_dist.h:_S_nd, 32-bit generator -> 64-bit product).
+// Both are restated here from their published definitions (Matsumoto & Nishimura 1998;
+// Lemire 2019) and pinned against libstdc++ in tests/.
+//
+// A stream is parsed into candidates: candidate k starts where candidate k-1 stopped.
+// Nearly all candidates consume exactly 8 words, so a block parses 256 candidates in
+// parallel by iterating "assume previous extras -> parse -> prefix-sum the extras" to a
+// fixed point (usually 1-2 passes).
+#pragma once
+#include "pose_math.cuh"
+
+namespace dsac {
+
+constexpr int MT_N = 624;
+constexpr int MT_M = 397;
+
+DSAC_HD uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+DSAC_HD uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+    uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+DSAC_HD void mt_seed(uint32_t* mt, uint32_t seed) {
+    mt[0] = seed;
+    for (int i = 1; i < MT_N; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+}
+
+// Sequential twist (host tests / reference for the block-parallel version below).
+DSAC_HD void mt_twist_all_seq(uint32_t* mt) {
+    for (int k = 0; k < MT_N - MT_M; k++) mt[k] = mt_twist(mt[k], mt[k + 1], mt[k + MT_M]);
+    for (int k = MT_N - MT_M; k < MT_N - 1; k++) mt[k] = mt_twist(mt[k], mt[k + 1], mt[k + MT_M - MT_N]);
+    mt[MT_N - 1] = mt_twist(mt[MT_N - 1], mt[0], mt[MT_M - 1]);
+}
+
+// A window of tempered stream words addressed by absolute stream position.
+struct WordRing {
+    const uint32_t* buf;
+    uint32_t mask;  // size-1, size a power of two
+    DSAC_HD uint32_t at(uint32_t pos) const { return buf[pos & mask]; }
+};
+
+// One libstdc++ uniform_int_distribution<int>(0, 39) draw starting at stream position
+// *pos; advances *pos past the words it consumed.
+DSAC_HD int lemire40(const WordRing& ring, uint32_t* pos) {
+    const uint32_t range = DSAC_GRID_CONST;
+    uint64_t product = (uint64_t)ring.at((*pos)++) * range;
+    uint32_t low = (uint32_t)product;
+    if (low < range) {
+        const uint32_t threshold = (0u - range) % range;  // 2^32 mod 40 = 16
+        while (low < threshold) {
+            product = (uint64_t)ring.at((*pos)++) * range;
+            low = (uint32_t)product;
+        }
+    }
+    return (int)(product >> 32);
+}
+
+// Parses the candidate starting at `start`: 4 distinct cells (x,y drawn in that order),
+// returns the number of words consumed.  Never reads at or beyond `limit`
+// (returns 0 if the candidate does not fit).
+DSAC_HD uint32_t parse_candidate(const WordRing& ring, uint32_t start, uint32_t limit, int cell[4]) {
+    uint32_t pos = start;
+    int n = 0;
+    while (n < 4) {
+        if (limit - pos < 2 + 2) return 0;  // keep a safety margin for Lemire re-draws
+        int x = lemire40(ring, &pos);
+        int y = lemire40(ring, &pos);
+        int c = y * DSAC_GRID_CONST + x;
+        bool dup = false;
+        for (int j = 0; j < 4; j++)
+            if (j < n && cell[j] == c) dup = true;
+        if (dup) continue;
+        cell[n++] = c;
+    }
+    return pos - start;
+}
+
+// libgomp static schedule of `#pragma omp parallel for` over h (cnn_softam.h:1010):
+// stream s of T owns a contiguous chunk; the first H%T streams get one more.
+DSAC_HD void stream_chunk(int H, int T, int s, int* h0, int* cnt) {
+    int q = H / T, r = H % T;
+    *cnt = q + (s < r ? 1 : 0);
+    *h0 = s * q + (s < r ? s : r);
+}
+
+}  // namespace dsac
