@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- hypotheses scored / second on synthetic 640x480 scene-coordinate maps.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: launched by torchrun, one rank per GPU; frames shard with no data-path collective)
+
+A step = one pass of the hot path (sample -> HxN reprojection errors -> soft-inlier score ->
+softmax / soft-argmax -> refinement -> evaluation) over one batch of frames per GPU.
+Workload (config.workload): BASELINE.json config 4's batch on every GPU -- 1024 frames x 256
+hypotheses x 40x40 points per GPU (weak scaling); the single-frame config 2 latency is reported
+beside it under "single_frame".  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+H = 256
+NPTS = 1600
+FRAMES_PER_GPU = 1024
+BYTES_F = NPTS * (6 + 8) + H * (48 + 8) + 56           # fused, scores only   
+BYTES_M = BYTES_F + H * NPTS * 4                       # diffmap materialised (reference behaviour)
+FLOPS_PER_PAIR = 38
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_cpu_sample(n_frames, threads, frame0=0):
+    """The oracle (CPU restatement of the reference path) on `n_frames` frames of the SAME workload."""
+    import dsac_b200.engine as E
+    from oracle import oracle as O
+    coords, pix, _, _ = E.synth_frames(n_frames, frame0=frame0)
+    cfg = O.default_config(seed=1305 + frame0)
+    secs = O.bench_forward(cfg, coords, pix, n_threads=threads, with_refine=True)
+    return n_frames * H / secs, secs
+
+
+def reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be
+    built here (OpenCV C++/Lua/Torch7/png++ missing), so this is the oracle port on all host threads."""
+    if rank != 0:
+        return
+    threads = cpu_threads()
+    per_step = max(threads * 2, 64)
+    for _ in range(args.warmup):
+        run_cpu_sample(max(threads, 16), threads)
+    t = 0.0
+    for s in range(args.steps):
+        _, secs = run_cpu_sample(per_step, threads, frame0=s * per_step)
+        t += secs
+    value = per_step * H * args.steps / t
+    sample = "%d frames/step x %d hyp x 1600 pts (same generator, seeds and config as the GPU arm), %d threads" % (per_step, H, threads)
+    line = {
+        "impl": "reference", "metric": "hypotheses scored/sec (256 hyp x 1600 pts/img)", "value": value, "unit": "hyp/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config4-shaped batch, CPU sample: " + sample, "n_hyps": H, "points": NPTS,
+                   "stages": "sample+score+softargmax+refine+eval"},
+        "cpu_baseline": {"value": value, "unit": "hyp/s", "cores": threads, "kind": "port", "sample": sample, "cpu": cpu_model()},
+        "e2e": {"value": value, "unit": "hyp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import dsac_b200.engine as E
+    from dsac_b200.sharding import shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nf = args.frames
+    n_total = nf * world
+    lo, hi = shard_range(n_total, rank, world)          # weak scaling: every rank owns `nf` frames
+    frame0 = lo
+    coords, pix, gt_cv, gt_jp = E.synth_frames(nf, frame0=frame0)
+    eng = E.Engine(max_frames=nf, device=local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # inputs resident in HBM for `value`
+    d_coords = torch.from_numpy(coords).cuda()
+    d_pix = torch.from_numpy(pix).cuda()
+    d_gt = torch.from_numpy(gt_jp).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # 2x the 126 MB L2
+
+    def step_device():
+        eng.forward_device(nf, d_coords.data_ptr(), d_pix.data_ptr(), 0, d_gt.data_ptr(), frame0, stream)
+
+    def timed_steps(fn, k):
+        """k steps, each bracketed by its own CUDA events on the launching stream, L2 flushed between."""
+        tot = 0.0
+        for _ in range(k):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot
+
+    eng.set_stages(E.STAGE_ALL)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launches
+    ms_total = timed_steps(step_device, args.steps)
+    gpu_launches = eng.launches - launches0
+    barrier()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = n_total * H * args.steps / (ms_total * 1e-3)
+
+    # quality of the result (pose error vs the generating pose)
+    res = eng.fetch(nf)
+    quality = {"accuracy_5cm5deg": float(res.correct.mean()), "median_rot_deg": float(np.median(res.rot_err)),
+               "median_t_mm": float(np.median(res.t_err)), "candidates_per_frame": float(res.n_candidates.mean()),
+               "frames_with_status": int((res.status != 0).sum())}
+
+    # ---- e2e: HOST (pinned) buffers through dsac_forward, H2D + kernels + D2H every step
+    def pinned(a):
+        t_ = torch.from_numpy(a).pin_memory()
+        return t_, t_.numpy()
+    k1, h_coords = pinned(coords); k2, h_pix = pinned(pix); k3, h_gt = pinned(gt_jp)
+    out = E.ForwardResult(nf, H, False)
+    keep = []
+    d2h = 0
+    for name in ("ref_pose", "avg_pose", "sf", "scores", "entropy", "loss", "rot_err", "t_err", "correct", "status", "n_candidates"):
+        tt, arr = pinned(getattr(out, name))
+        keep.append(tt)
+        setattr(out, name, arr)
+        setattr(out.raw, name, arr.ctypes.data)
+        d2h += arr.nbytes
+    for name in ("hyp_pose", "img_idx", "cand_idx", "diffmaps", "inlier_map", "ref_steps_done", "n_perm_steps"):
+        setattr(out.raw, name, None)
+    h2d = h_coords.nbytes + h_pix.nbytes + h_gt.nbytes
+
+    def step_host():
+        eng.forward(h_coords, h_pix, h_gt, frame0=frame0, out=out)
+
+    for _ in range(max(args.warmup, 3)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * H * args.steps / float(t.item())
+    clk = clocks.stop() if clocks else None
+
+    # ---- per-stage kernel durations (stage-isolated launches, CUDA events) and the K2 roofline
+    stage_ms = {}
+    for name, mask in (("k_sample", E.STAGE_SAMPLE), ("k_score", E.STAGE_SCORE), ("k_refine", E.STAGE_REFINE | E.STAGE_EVAL)):
+        eng.set_stages(E.STAGE_ALL)
+        step_device()
+        eng.set_stages(mask)
+        step_device()
+        torch.cuda.synchronize()
+        stage_ms[name] = timed_steps(step_device, max(3, min(args.steps, 10))) / max(3, min(args.steps, 10))
+    eng.set_stages(E.STAGE_ALL)
+    peak, peak_src = peaks()
+    k2_s = stage_ms["k_score"] * 1e-3
+    achieved = BYTES_M * nf / k2_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k_score_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    ssum = sum(stage_ms.values())
+    roofline = {"kernel": "k_score<write_diffmaps=1> (HxN reprojection-error matrix + soft-inlier score + soft-argmax tail)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_M * nf,
+                "ms_per_launch": stage_ms["k_score"], "share_of_step": stage_ms["k_score"] / ssum,
+                "fp32_gflops": FLOPS_PER_PAIR * H * NPTS * nf / k2_s / 1e9}
+
+    # ---- config 2: single frame latency (1 frame, 256 hyp, forward scoring + soft-argmax)
+    single = None
+    if rank == 0:
+        eng1 = E.Engine(max_frames=1, device=local_rank)
+        eng1.set_stages(E.STAGE_SAMPLE | E.STAGE_SCORE)
+        for _ in range(20):
+            eng1.forward_device(1, d_coords.data_ptr(), d_pix.data_ptr(), 0, d_gt.data_ptr(), frame0, stream)
+        torch.cuda.synchronize()
+        reps = 200
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            eng1.forward_device(1, d_coords.data_ptr(), d_pix.data_ptr(), 0, d_gt.data_ptr(), frame0, stream)
+        e1.record()
+        e1.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        single = {"workload": "config 2: 1 frame x 256 hyp x 1600 pts, sample+score+soft-argmax", "latency_us": us,
+                  "hyp_per_s": H / (us * 1e-6)}
+        eng1.close()
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
+    cpu = None
+    if rank == 0 and world == 1:
+        threads = cpu_threads()
+        ncpu = args.cpu_frames or max(256, 2 * threads)
+        run_cpu_sample(min(ncpu, threads), threads)       # warm the library / page in
+        v, secs = run_cpu_sample(ncpu, threads)
+        cpu = {"value": v, "unit": "hyp/s", "cores": threads, "kind": "port",
+               "sample": "first %d of the %d frames x %d hyp x 1600 pts, full pipeline, %.2f s wall (%.1f s CPU)" % (ncpu, nf, H, secs, secs * min(threads, ncpu)),
+               "cpu": cpu_model(), "note": "oracle = CPU restatement with closed-form score; omits the reference's Lua/cuDNN round trip"}
+
+    if rank == 0:
+        line = {
+            "metric": "hypotheses scored/sec (256 hyp x 1600 pts/img)", "value": value, "unit": "hyp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (P3P, softmax, LM) + f32 (HxN matrix, scores)",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE config 4 batch per GPU: %d frames x %d hyp x 40x40 pts (640x480, f=525), full test pipeline "
+                                   "sample+score+softargmax+refine+eval, diffmaps materialised" % (nf, H),
+                       "frames_per_gpu": nf, "n_hyps": H, "points": NPTS, "streams_per_frame": 1, "inlier_ratio": 0.5,
+                       "noise_mm": 25.0, "data_seed": 20170721, "sampler_seed": 1305, "alpha": 0.1, "beta": 0.5,
+                       "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+                       "l2": "256 MB buffer written between timed steps (flush); each step also streams %.2f GB of diffmaps" % (BYTES_M * nf / 1e9)},
+            "e2e": {"value": e2e_value, "unit": "hyp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * float(t.item()) / args.steps,
+                    "api": "dsac_forward (host pinned buffers -> H2D -> kernels -> D2H of poses/scores/errors)"},
+            "gpu_launches": gpu_launches,
+            "roofline": roofline,
+            "kernels_ms": stage_ms,
+            "cpu_baseline": cpu,
+            "single_frame": single,
+            "quality": quality,
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
