@@ -221,6 +221,7 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         }
         CUC(cudaMemcpy(e->d_perm, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
+    CUC(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
     e->h_stream_ncand.resize(n * cfg->n_streams);
 #undef CUC
     *out = e;
@@ -280,7 +281,7 @@ int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
         sp.frame0 = frame0;
         sp.hyp_pose = e->d_hyp_pose; sp.hyp_P = e->d_hyp_P; sp.img_idx = e->d_img_idx; sp.cand_idx = e->d_cand_idx;
         sp.stream_ncand = e->d_stream_ncand; sp.status = e->d_status; sp.n_fragile = e->d_fragile;
-        k_sample<<<dim3(c.n_streams, n), K1_THREADS, 0, stream>>>(sp);
+        k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);
         e->launches++;
         CU(cudaGetLastError());
     }

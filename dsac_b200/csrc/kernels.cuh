@@ -17,7 +17,8 @@
 namespace dsac {
 
 // ------------------------------------------------------------------ block helpers
-// Exclusive prefix sum over a 256-thread block (+ block total).  Two barriers.
+// Exclusive prefix sum over a 256-thread block (+ block total).  One barrier: consecutive calls must
+// use different s_warp buffers.
 __device__ __forceinline__ int block_excl_scan_256(int v, int* total, int* s_warp /* >= 8 ints */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = v;
@@ -26,8 +27,7 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* total, int* s_war
         int n = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += n;
     }
-    __syncthreads();  // protect s_warp reuse
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 31) s_warp[warp] = incl;   // callers alternate between two s_warp buffers
     __syncthreads();
     int base = 0, tot = 0;
 #pragma unroll
@@ -60,48 +60,93 @@ struct SampleParams {
 };
 
 constexpr int K1_THREADS = 256;
-constexpr int K1_RING = 4096;          // words; >= 2048 + margin + 623
-constexpr int K1_NEED = 2048 + 128;    // words that must be available past `pos` before a round
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 2
+#endif
+constexpr int K1_SUPER_MAX = 16;                          // x256 candidates per super-round
+constexpr int K1_CANDS = K1_SUPER_MAX * K1_THREADS;       // candidates buffered per super-round
+constexpr int K1_WORDS = K1_CANDS * 8 + 1024;             // decoded stream words buffered per super-round
+constexpr int K1_WAVE = MT_N - MT_M;                      // 227 new MT19937 words per barrier
+constexpr int K1_SEGS = 32, K1_WALK = 8;                  // chain walkers: 32 segments x 8 entry offsets
 
-__device__ __forceinline__ void mt_twist_block(uint32_t* mt, uint32_t* ring, uint32_t out_base) {
-    const int tid = threadIdx.x;
-    uint32_t v = 0;
-    // phase 1: k in [0,227) depends on old state only
-    if (tid < MT_N - MT_M) v = mt_twist(mt[tid], mt[tid + 1], mt[tid + MT_M]);
-    __syncthreads();
-    if (tid < MT_N - MT_M) {
-        mt[tid] = v;
-        ring[(out_base + tid) & (K1_RING - 1)] = mt_temper(v);
+// Per-cell record staged in shared memory: scene coordinate (mm) and the float-rounded
+// normalised pixel that cv::undistortPoints hands to P3P.
+struct __align__(16) CellRec {
+    short X, Y, Z, pad;
+    float xn, yn;
+};
+
+struct K1Smem {
+    CellRec cell[DSAC_N_CONST];
+    uint32_t st[1024];                          // sliding window of the raw MT19937 sequence (linear index & 1023)
+    __align__(4) unsigned char vals[K1_WORDS];  // Lemire value (0..39) of stream word pos+i; 255 = rejected draw
+    unsigned char elen[K1_WORDS / 2];           // words consumed by a candidate starting at even offset 2i (0 = does not fit)
+    unsigned short cand_start[K1_CANDS + 512];    // word offset (from pos) where candidate i starts
+    unsigned short q_idx[K1_CANDS];             // queue of candidates that need the full solve, ascending
+    uint32_t flagbits[K1_CANDS / 32];
+    uint32_t wordbase[K1_CANDS / 32];
+    unsigned short wk_exit[K1_SEGS * K1_WALK];
+    unsigned short wk_cnt[K1_SEGS * K1_WALK];
+    unsigned short seg_base[K1_SEGS + 1];
+    unsigned char seg_sel[K1_SEGS];
+    int warp[2][8];
+    int q_n, n_sr, any_reject, walk_fail;
+};
+
+// 4 distinct cells (x, y drawn in that order, a repeated cell is re-drawn: cnn_softam.h:1021-1039)
+// from the decoded value stream starting at word offset q; returns the offset after the candidate,
+// or -1 if the buffered words run out.  255 marks a word libstdc++'s Lemire loop rejects.
+__device__ __forceinline__ int cand_parse(const unsigned char* vals, int q, int limit, int cells[4]) {
+    int n = 0;
+    while (n < 4) {
+        int vx, vy;
+        do {
+            if (q >= limit) return -1;
+            vx = vals[q++];
+        } while (vx == 255);
+        do {
+            if (q >= limit) return -1;
+            vy = vals[q++];
+        } while (vy == 255);
+        int c = vy * DSAC_GRID_CONST + vx;
+        bool dup = false;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            if (j < n && cells[j] == c) dup = true;
+        if (!dup) cells[n++] = c;
     }
-    __syncthreads();
-    // phase 2: k in [227,454) uses the new words [0,227)
-    int k = MT_N - MT_M + tid;
-    if (tid < MT_N - MT_M) v = mt_twist(mt[k], mt[k + 1], mt[k - (MT_N - MT_M)]);
-    __syncthreads();
-    if (tid < MT_N - MT_M) {
-        mt[k] = v;
-        ring[(out_base + k) & (K1_RING - 1)] = mt_temper(v);
-    }
-    __syncthreads();
-    // phase 3: k in [454,624) uses the new words [227,397); the last word wraps to new mt[0]
-    k = 2 * (MT_N - MT_M) + tid;
-    if (k < MT_N - 1) v = mt_twist(mt[k], mt[k + 1], mt[k - (MT_N - MT_M)]);
-    else if (k == MT_N - 1) v = mt_twist(mt[MT_N - 1], mt[0], mt[MT_M - 1]);
-    __syncthreads();
-    if (k < MT_N) {
-        mt[k] = v;
-        ring[(out_base + k) & (K1_RING - 1)] = mt_temper(v);
-    }
-    __syncthreads();
+    return q;
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k_sample(SampleParams p) {
-    __shared__ uint32_t s_mt[MT_N];
-    __shared__ uint32_t s_ring[K1_RING];
-    __shared__ int s_warp[8];
-    __shared__ uint32_t s_newpos;
+// Common case of cand_parse in ~25 instructions: 8 words at an even offset, no rejected draw, 4 distinct
+// cells.  Falls back to the generic parser otherwise.
+__device__ __forceinline__ int cand_parse_fast(const unsigned char* vals, int q, int limit, int cells[4]) {
+    if (q + 8 <= limit && !(q & 1)) {
+        const unsigned short* v16 = reinterpret_cast<const unsigned short*>(vals + q);
+        const unsigned a0 = v16[0], a1 = v16[1], a2 = v16[2], a3 = v16[3];   // (y << 8) | x
+        const unsigned any = a0 | a1 | a2 | a3;      // values are <= 39 or exactly 255: bit 7 set <=> some byte is 255
+        const int c0 = (a0 >> 8) * DSAC_GRID_CONST + (a0 & 255), c1 = (a1 >> 8) * DSAC_GRID_CONST + (a1 & 255);
+        const int c2 = (a2 >> 8) * DSAC_GRID_CONST + (a2 & 255), c3 = (a3 >> 8) * DSAC_GRID_CONST + (a3 & 255);
+        const bool distinct = (c0 != c1) & (c0 != c2) & (c0 != c3) & (c1 != c2) & (c1 != c3) & (c2 != c3);
+        if (!(any & 0x8080u) && distinct) {
+            cells[0] = c0; cells[1] = c1; cells[2] = c2; cells[3] = c3;
+            return q + 8;
+        }
+    }
+    return cand_parse(vals, q, limit, cells);
+}
 
-    const int tid = threadIdx.x;
+// One CTA per (frame, stream).  Per super-round of up to S x 256 candidates:
+//   A  MT19937 in waves of 227 words (one barrier each), every word decoded on the fly to its
+//      uniform_int_distribution value; candidate boundaries by 256 speculative chain walkers
+//   B  cheap conservative filter, one thread per candidate, no block barriers
+//   C  queue the ~2% that need the full fp64 P3P, in candidate order
+//   D  full solve + reprojection check on the queue, ordered compaction of the accepted
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SampleParams p) {
+    extern __shared__ __align__(16) unsigned char k1_smem_raw[];
+    K1Smem& sm = *reinterpret_cast<K1Smem*>(k1_smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31;
     const int s = blockIdx.x, frame = blockIdx.y;
     int h0, quota;
     stream_chunk(p.H, p.T, s, &h0, &quota);
@@ -111,92 +156,267 @@ __global__ void __launch_bounds__(K1_THREADS) k_sample(SampleParams p) {
     }
 
     // stream s of global frame g: mt19937(seed + g*T + s)   (thread_rand.cpp:52 for g = 0)
-    if (tid == 0) mt_seed(s_mt, p.seed + (uint32_t)((p.frame0 + frame) * (long long)p.T + s));
-    __syncthreads();
+    if (tid == 0) mt_seed(sm.st, p.seed + (uint32_t)((p.frame0 + frame) * (long long)p.T + s));
 
     const int16_t* coords = p.coords + (size_t)frame * DSAC_N_CONST * 3;
     const int32_t* pix = p.pix + (size_t)frame * p.pix_stride;
-    WordRing ring{s_ring, K1_RING - 1};
+    {
+        const double inv_f = 1. / p.f;
+        for (int c = tid; c < DSAC_N_CONST; c += K1_THREADS) {
+            CellRec r;
+            r.X = __ldg(coords + c * 3); r.Y = __ldg(coords + c * 3 + 1); r.Z = __ldg(coords + c * 3 + 2); r.pad = 0;
+            r.xn = (float)(((double)(float)__ldg(pix + c * 2) - p.cx) * inv_f);      // == p3p_pixel's rounding
+            r.yn = (float)(((double)(float)__ldg(pix + c * 2 + 1) - p.cy) * inv_f);
+            sm.cell[c] = r;
+        }
+    }
+    if (tid == 0) { sm.any_reject = 0; sm.walk_fail = 0; }
+    __syncthreads();
 
-    uint32_t pos = (s == 0) ? p.skip : 0u;  // stream position of the next unread word
-    uint32_t gen = 0;                       // words generated so far
+    uint32_t pos = (s == 0) ? p.skip : 0u;  // stream position (output word index) of the next unread word
+    uint32_t gen = 0;                       // output words generated so far (linear MT index = gen + 624)
     int acc = 0;                            // hypotheses accepted so far
     long long cand_base = 0;                // candidates consumed so far
     const long long cand_max = p.max_candidates > 0 ? (long long)p.max_candidates : (1ll << 40);
+    int S = 4;                              // x256 candidates in the next super-round (adapted to the acceptance rate)
+
+    auto load_problem = [&](const int cells[4], P3PProblem& pr) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const CellRec r = sm.cell[cells[j]];
+            pr.mu[j] = r.xn * p.f + p.cx;   // float * double, as p3p_pixel
+            pr.mv[j] = r.yn * p.f + p.cy;
+            pr.X[j][0] = (double)r.X; pr.X[j][1] = (double)r.Y; pr.X[j][2] = (double)r.Z;
+        }
+    };
 
     while (acc < quota && cand_base < cand_max) {
-        while ((int)(gen - pos) < K1_NEED) {
-            mt_twist_block(s_mt, s_ring, gen);
-            gen += MT_N;
-        }
-        // ---- parse up to 256 candidates starting at pos (fixed point over the extras)
-        int extra = 0, cells[4];
-        uint32_t start, consumed;
-        for (;;) {
-            int tot;
-            int excl = block_excl_scan_256(extra, &tot, s_warp);
-            start = pos + 8u * tid + (uint32_t)excl;
-            consumed = parse_candidate(ring, start, gen, cells);
-            int ne = consumed ? (int)consumed - 8 : 0;
-            int changed = (ne != extra);
-            extra = ne;
-            if (!__syncthreads_or(changed)) break;
-        }
-        // candidates that did not fit in the generated window (practically never) wait for the next round
-        int bad = (consumed == 0) ? tid : K1_THREADS;
-#pragma unroll
-        for (int off = 16; off; off >>= 1) bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, off));
-        __syncthreads();
-        if ((tid & 31) == 0) s_warp[tid >> 5] = bad;
-        __syncthreads();
-        int n_valid = K1_THREADS;
-#pragma unroll
-        for (int w = 0; w < 8; w++) n_valid = min(n_valid, s_warp[w]);
-        if (cand_max - cand_base < n_valid) n_valid = (int)(cand_max - cand_base);
-        if (tid == n_valid - 1) s_newpos = start + consumed;
-        // (n_valid == 0 cannot happen: K1_NEED words always hold at least one candidate)
-
-        // ---- evaluate: fp64 P3P + reprojection check (cnn_softam.h:1041-1059)
-        bool ok = false, fragile = false;
-        double rvec[3], tvec[3];
-        if (tid < n_valid) {
-            float obj[12], img[8];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int c = cells[j];
-                img[j * 2] = (float)__ldg(pix + c * 2);
-                img[j * 2 + 1] = (float)__ldg(pix + c * 2 + 1);
-                obj[j * 3] = (float)__ldg(coords + c * 3);
-                obj[j * 3 + 1] = (float)__ldg(coords + c * 3 + 1);
-                obj[j * 3 + 2] = (float)__ldg(coords + c * 3 + 2);
+        // ---------------- phase A1: generate + decode words until the super-round's window is full
+        long long want = (long long)S * K1_THREADS;
+        if (cand_max - cand_base < want) want = cand_max - cand_base;
+        const int n_target = (int)want;
+        const int w_need = min(K1_WORDS - 256, n_target * 8 + 768);   // a wave may overshoot by 226 words
+        // (leftover words [pos, gen) were moved to vals[0..gen-pos) at the end of the previous super-round)
+        while ((int)(gen - pos) < w_need) {
+            if (tid < K1_WAVE) {
+                uint32_t n = gen + MT_N + tid;  // linear index of the new element
+                uint32_t x = mt_twist(sm.st[(n - MT_N) & 1023], sm.st[(n - MT_N + 1) & 1023], sm.st[(n - K1_WAVE) & 1023]);
+                sm.st[n & 1023] = x;
+                int off = (int)(gen + tid - pos);
+                if (off >= 0 && off < K1_WORDS) {
+                    uint64_t prod = (uint64_t)mt_temper(x) * DSAC_GRID_CONST;
+                    bool rej = (uint32_t)prod < ((0u - DSAC_GRID_CONST) % DSAC_GRID_CONST);  // Lemire: low < 2^32 mod 40
+                    sm.vals[off] = rej ? (unsigned char)255 : (unsigned char)(prod >> 32);
+                    if (rej) sm.any_reject = 1;
+                }
             }
-            ok = minimal_set_hypothesis(obj, img, p.f, p.cx, p.cy, p.thr, rvec, tvec, &fragile);
+            gen += K1_WAVE;
+            __syncthreads();
         }
-        if (fragile) atomicAdd(p.n_fragile, 1ull);
+        const int w_avail = min((int)(gen - pos), K1_WORDS);
 
-        // ---- ordered compaction: the first `quota` accepted candidates of the stream
-        int tot;
-        int rank = acc + block_excl_scan_256(ok ? 1 : 0, &tot, s_warp);
-        if (ok && rank < quota) {
-            size_t hi = (size_t)frame * p.H + h0 + rank;
-            double* hp = p.hyp_pose + hi * 6;
-            hp[0] = rvec[0]; hp[1] = rvec[1]; hp[2] = rvec[2];
-            hp[3] = tvec[0]; hp[4] = tvec[1]; hp[5] = tvec[2];
-            double R[9];
-            rodrigues_v2m(rvec, R);  // getDiffMap -> cv::projectPoints rebuilds R from rvec
-            float4* P = reinterpret_cast<float4*>(p.hyp_P + hi * 12);
-            P[0] = make_float4((float)(p.f * R[0]), (float)(p.f * R[1]), (float)(p.f * R[2]), (float)(p.f * tvec[0]));
-            P[1] = make_float4((float)(p.f * R[3]), (float)(p.f * R[4]), (float)(p.f * R[5]), (float)(p.f * tvec[1]));
-            P[2] = make_float4((float)R[6], (float)R[7], (float)R[8], (float)tvec[2]);
-            int4 ii = make_int4(cells[0], cells[1], cells[2], cells[3]);
-            *reinterpret_cast<int4*>(p.img_idx + hi * 4) = ii;
-            p.cand_idx[hi] = (int32_t)(cand_base + tid);
-            if (rank == quota - 1) p.stream_ncand[(size_t)frame * p.T + s] = cand_base + tid + 1;
+        // ---------------- phase A2: candidate boundaries.  A candidate is 8 words long unless a cell repeats
+        // (+2 words) or a draw is rejected (+1).  (i) every even offset gets the length of the candidate that
+        // would start there; (ii) thread (m, c) follows the chain through segment m assuming it enters at
+        // offset 2c; (iii) the true chain is stitched from the matching walkers and written out.
+        for (int i = tid * 2; i < w_avail; i += K1_THREADS * 2) {
+            int cells[4];
+            int qn = cand_parse_fast(sm.vals, i, w_avail, cells);
+            sm.elen[i >> 1] = (qn < 0) ? (unsigned char)0 : (unsigned char)(qn - i);
         }
-        acc += tot;
-        cand_base += n_valid;
         __syncthreads();
-        pos = s_newpos;
+        const int seg_len = ((w_need / K1_SEGS) + 7) & ~7;
+        {
+            const int m = tid / K1_WALK, c = tid % K1_WALK;
+            int q = m * seg_len + 2 * c, cnt = 0;
+            const int seg_end = min((m + 1) * seg_len, w_avail);
+            while (q < seg_end) {
+                int l = sm.elen[q >> 1];
+                if (l == 0 || (l & 1)) break;   // window exhausted / odd length: only the sequential path handles it
+                q += l;
+                cnt++;
+            }
+            sm.wk_exit[tid] = (unsigned short)q;   // first chain position >= seg_end (or where the words ran out)
+            sm.wk_cnt[tid] = (unsigned short)cnt;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int q = 0, total = 0;
+            bool fail = sm.any_reject != 0;
+            for (int m = 0; m < K1_SEGS && !fail; m++) {
+                sm.seg_base[m] = (unsigned short)total;
+                int off = q - m * seg_len;
+                if (off < 0 || q >= min((m + 1) * seg_len, w_avail)) { sm.seg_sel[m] = 255; continue; }  // chain ended earlier
+                if ((off & 1) || off >= 2 * K1_WALK) { fail = true; break; }
+                sm.seg_sel[m] = (unsigned char)(off >> 1);
+                total += sm.wk_cnt[m * K1_WALK + (off >> 1)];
+                q = sm.wk_exit[m * K1_WALK + (off >> 1)];
+            }
+            sm.seg_base[K1_SEGS] = (unsigned short)total;
+            if (fail) {  // rejected draw in the window (p ~ 1e-4 per super-round) or >7 repeats: plain sequential walk
+                q = 0; total = 0;
+                while (total < K1_CANDS + 500) {
+                    int cells[4];
+                    int qn = cand_parse(sm.vals, q, w_avail, cells);
+                    if (qn < 0) break;
+                    sm.cand_start[total++] = (unsigned short)q;
+                    q = qn;
+                }
+                sm.cand_start[total] = (unsigned short)q;
+                sm.walk_fail = 1;
+            }
+            sm.n_sr = min(total, n_target);
+        }
+        __syncthreads();
+        if (!sm.walk_fail && (tid % K1_WALK) == 0) {   // re-walk the selected chains and record the starts
+            const int m = tid / K1_WALK;
+            const int sel = sm.seg_sel[m];
+            if (sel != 255) {
+                int q = m * seg_len + 2 * sel, idx = sm.seg_base[m];
+                const int seg_end = min((m + 1) * seg_len, w_avail);
+                while (q < seg_end) {
+                    int l = sm.elen[q >> 1];
+                    if (l == 0) break;
+                    sm.cand_start[idx++] = (unsigned short)q;
+                    q += l;
+                }
+                if (idx == sm.seg_base[K1_SEGS]) sm.cand_start[idx] = (unsigned short)q;  // end of the last candidate
+            }
+        }
+        __syncthreads();
+        const int n_sr = sm.n_sr;
+
+        // ---------------- phase B: conservative filter, warps run without block barriers
+        for (int i0 = 0; i0 < n_sr; i0 += K1_THREADS) {
+            const int i = i0 + tid;
+            bool need = false;
+            if (i < n_sr) {
+                int cells[4];
+                cand_parse_fast(sm.vals, sm.cand_start[i], w_avail, cells);
+                P3PProblem pr;
+                load_problem(cells, pr);
+                need = minimal_set_needs_full_pr(pr, p.f, p.cx, p.cy, p.thr);
+            }
+            uint32_t bits = __ballot_sync(0xffffffffu, need);
+            if (lane == 0) sm.flagbits[i >> 5] = bits;
+        }
+        __syncthreads();
+
+        // ---------------- phase C: queue of flagged candidates in candidate order
+        const int n_words = (n_sr + 31) >> 5;   // <= 128
+        if (tid < 32) {
+            int cnt[4], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int w = tid * 4 + k;
+                cnt[k] = (w < n_words) ? __popc(sm.flagbits[w]) : 0;
+                sum += cnt[k];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int nb = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += nb;
+            }
+            int run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int w = tid * 4 + k;
+                if (w < n_words) sm.wordbase[w] = run;
+                run += cnt[k];
+            }
+            if (tid == 31) sm.q_n = incl;
+        }
+        __syncthreads();
+        for (int i = tid; i < n_sr; i += K1_THREADS) {
+            uint32_t wbits = sm.flagbits[i >> 5];
+            if ((wbits >> (i & 31)) & 1u)
+                sm.q_idx[sm.wordbase[i >> 5] + __popc(wbits & ((1u << (i & 31)) - 1u))] = (unsigned short)i;
+        }
+        __syncthreads();
+        const int q_n = sm.q_n;
+
+        // ---------------- phase D: full fp64 P3P + reprojection check (cnn_softam.h:1041-1059) on the
+        //                  queue, then the first `quota` accepted candidates of the stream, in order
+        int par = 0;
+        for (int base = 0; base < q_n && acc < quota; base += K1_THREADS, par ^= 1) {
+            const int qi = base + tid;
+            bool ok = false, fragile = false;
+            double rvec[3], tvec[3];
+            int cells[4] = {0, 0, 0, 0};
+            long long cand = 0;
+            if (qi < q_n) {
+                int ci = sm.q_idx[qi];
+                cand_parse_fast(sm.vals, sm.cand_start[ci], w_avail, cells);
+                cand = cand_base + ci;
+                P3PProblem pr;
+                load_problem(cells, pr);
+                float obj[12], img[8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    obj[j * 3] = (float)pr.X[j][0]; obj[j * 3 + 1] = (float)pr.X[j][1]; obj[j * 3 + 2] = (float)pr.X[j][2];
+                    img[j * 2] = (float)__ldg(pix + cells[j] * 2);
+                    img[j * 2 + 1] = (float)__ldg(pix + cells[j] * 2 + 1);
+                }
+                ok = minimal_set_hypothesis_pr(pr, obj, img, p.f, p.cx, p.cy, p.thr, rvec, tvec, &fragile);
+            }
+            if (fragile) atomicAdd(p.n_fragile, 1ull);
+            int tot;
+            int rank = acc + block_excl_scan_256(ok ? 1 : 0, &tot, sm.warp[par]);
+            if (ok && rank < quota) {
+                size_t hi = (size_t)frame * p.H + h0 + rank;
+                double* hp = p.hyp_pose + hi * 6;
+                hp[0] = rvec[0]; hp[1] = rvec[1]; hp[2] = rvec[2];
+                hp[3] = tvec[0]; hp[4] = tvec[1]; hp[5] = tvec[2];
+                double R[9];
+                rodrigues_v2m(rvec, R);  // getDiffMap -> cv::projectPoints rebuilds R from rvec
+                float4* P = reinterpret_cast<float4*>(p.hyp_P + hi * 12);
+                P[0] = make_float4((float)(p.f * R[0]), (float)(p.f * R[1]), (float)(p.f * R[2]), (float)(p.f * tvec[0]));
+                P[1] = make_float4((float)(p.f * R[3]), (float)(p.f * R[4]), (float)(p.f * R[5]), (float)(p.f * tvec[1]));
+                P[2] = make_float4((float)R[6], (float)R[7], (float)R[8], (float)tvec[2]);
+                *reinterpret_cast<int4*>(p.img_idx + hi * 4) = make_int4(cells[0], cells[1], cells[2], cells[3]);
+                p.cand_idx[hi] = (int32_t)cand;
+                if (rank == quota - 1) p.stream_ncand[(size_t)frame * p.T + s] = cand + 1;
+            }
+            acc += tot;
+        }
+
+        // ---------------- advance the stream: the unread tail of the window moves to the front
+        {
+            const int consumed = sm.cand_start[n_sr];
+            const int left = w_avail - consumed;     // == gen - (pos + consumed) whenever w_avail == gen - pos
+            unsigned char keep[(K1_WORDS / K1_THREADS) + 1];
+            __syncthreads();
+            if (acc < quota) {
+#pragma unroll 1
+                for (int k = 0, i = tid; i < left; i += K1_THREADS, k++) keep[k] = sm.vals[consumed + i];
+            }
+            __syncthreads();
+            bool rej_left = false;
+            if (acc < quota) {
+#pragma unroll 1
+                for (int k = 0, i = tid; i < left; i += K1_THREADS, k++) {
+                    sm.vals[i] = keep[k];
+                    rej_left |= (keep[k] == 255);
+                }
+            }
+            if (tid == 0) { sm.any_reject = 0; sm.walk_fail = 0; }
+            __syncthreads();
+            if (rej_left) sm.any_reject = 1;   // a rejected draw carried over into the next window
+            pos += (uint32_t)consumed;
+            cand_base += n_sr;
+        }
+        // next super-round: as many candidates as the observed acceptance rate suggests are still needed
+        if (acc < quota) {
+            if (acc > 0) {
+                double need_c = (double)(quota - acc) * (double)cand_base / (double)acc * 1.1;
+                int r = (int)(need_c / K1_THREADS) + 1;
+                S = r < 1 ? 1 : (r > K1_SUPER_MAX ? K1_SUPER_MAX : r);
+            } else {
+                S = K1_SUPER_MAX;
+            }
+        }
+        __syncthreads();
     }
 
     if (acc < quota) {  // sampler exhausted: value-encode like a failed PnP (zero pose, cnn_softam.h:66-71)
@@ -247,9 +467,9 @@ __device__ __forceinline__ float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float fast_sqrt(float x) {
+__device__ __forceinline__ float fast_rsqrt(float x) {
     float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -317,7 +537,7 @@ __device__ void softargmax_tail(const ScoreParams& p, int frame, double* s_red /
 }
 
 template <bool WRITE_DM>
-__global__ void __launch_bounds__(K2_THREADS) k_score(ScoreParams p) {
+__global__ void __launch_bounds__(K2_THREADS, 3) k_score(ScoreParams p) {
     __shared__ __align__(16) float s_P[K2_MAX_TILE * 12];
     __shared__ float s_part[K2_WARPS][K2_MAX_TILE];
     __shared__ double s_red[8 * K2_WARPS];
@@ -366,19 +586,28 @@ __global__ void __launch_bounds__(K2_THREADS) k_score(ScoreParams p) {
                     const float4 r0 = *reinterpret_cast<const float4*>(s_P + h * 12);
                     const float4 r1 = *reinterpret_cast<const float4*>(s_P + h * 12 + 4);
                     const float4 r2 = *reinterpret_cast<const float4*>(s_P + h * 12 + 8);
+                    // Per point: ONE rsqrt gives the clamped reprojection error,
+                    //   e = |pix - proj| = sqrt(A)/|z|,  A = (pu*z - xs)^2 + (pv*z - ys)^2  ->  e = A * rsqrt(A * z^2),
+                    // and the sigmoids of two points share ONE reciprocal:
+                    //   1/(1+t1) + 1/(1+t2) = (2 + t1 + t2) / ((1+t1)(1+t2)),  t = 2^(kbeta*(e - tau)) clamped to 2^60.
+                    float t[K2_PTS];
 #pragma unroll
                     for (int j = 0; j < K2_PTS; j++) {
                         float xs = fmaf(r0.x, X[j], fmaf(r0.y, Y[j], fmaf(r0.z, Z[j], r0.w)));
                         float ys = fmaf(r1.x, X[j], fmaf(r1.y, Y[j], fmaf(r1.z, Z[j], r1.w)));
                         float zs = fmaf(r2.x, X[j], fmaf(r2.y, Y[j], fmaf(r2.z, Z[j], r2.w)));
-                        float iz = (zs != 0.f) ? fast_rcp(zs) : 1.f;  // z ? 1/z : 1 (cv::projectPoints)
-                        float du = fmaf(-xs, iz, pu[j]);
-                        float dv = fmaf(-ys, iz, pv[j]);
-                        float e = fast_sqrt(fmaf(du, du, dv * dv));
-                        e = fminf(e, DSAC_MAXINPUT_F);  // min(norm, CNN_OBJ_MAXINPUT), cnn_softam.h:357
+                        zs = (zs != 0.f) ? zs : 1.f;  // z ? 1/z : 1 (cv::projectPoints)
+                        float du = fmaf(pu[j], zs, -xs);
+                        float dv = fmaf(pv[j], zs, -ys);
+                        float A = fmaf(du, du, dv * dv);
+                        float e = A * fast_rsqrt(A * (zs * zs));
+                        e = (A > 0.f) ? fminf(e, DSAC_MAXINPUT_F) : 0.f;  // min(norm, CNN_OBJ_MAXINPUT), cnn_softam.h:357
                         if (WRITE_DM) __stcs(dm + (size_t)h * DSAC_N_CONST + tid + j * K2_THREADS, e);
-                        // sigmoid(beta*(tau-e)) = 1/(1+2^(kbeta*e - kbeta*tau))
-                        a += fast_rcp(1.f + fast_ex2(fmaf(p.kbeta, e, -tau_k)));
+                        t[j] = fminf(fast_ex2(fmaf(p.kbeta, e, -tau_k)), 1.152921504606847e18f);
+                    }
+                    {
+                        float d01 = (1.f + t[0]) * (1.f + t[1]), d23 = (1.f + t[2]) * (1.f + t[3]);
+                        a = (2.f + t[0] + t[1]) * fast_rcp(d01) + (2.f + t[2] + t[3]) * fast_rcp(d23) + fast_rcp(1.f + t[4]);
                     }
                 }
                 acc[u] = a;

@@ -183,36 +183,59 @@ DSAC_HD void pose_from_lengths(const double Lx, const double Ly, const double Lz
     for (int i = 0; i < 3; i++) t[i] = Cc[i] - (R[i * 3] * Cw[0] + R[i * 3 + 1] * Cw[1] + R[i * 3 + 2] * Cw[2]);
 }
 
-// All P3P solutions from points 0..2, the one with the smallest squared reprojection
-// error of point 3 is returned (cv::solvePnP CV_P3P semantics).  Returns the number of
-// solutions; *best_err2 is that smallest squared error (pixels^2).
-DSAC_HDN int p3p_best(const P3PProblem& pr, double f, double cx, double cy, double Rbest[9], double tbest[3],
-                      double* best_err2) {
-    double inv_f = 1.0 / f, cx_f = cx / f, cy_f = cy / f;
+// Front end shared by the quick filter and the full solve: bearings, the two quadrics'
+// coefficients and the closed-form roots of the quartic in x = |PA|/|PC|.
+struct P3PFront {
     double bear[3][3];
+    double p, q, r, a, b;       // quadrics: f1 = (1-a)y^2 - a x^2 - p y + a r x y + 1, f2 = (1-b)x^2 - b y^2 - q x + b r x y + 1
+    double N2, N1, N0, D1, D0;  // y * (D1 x + D0) = -(N2 x^2 + N1 x + N0)
+    double d01;
+    double xr[4];
+    int nroots;
+};
+
+#if defined(__CUDACC__) && !defined(DSAC_HOST_ONLY)
+#define DSAC_NOINLINE __noinline__
+#else
+#define DSAC_NOINLINE
+#endif
+
+// Not inlined on the device so that the quick filter and the full solve see bit-identical
+// roots (one compiled instance, one FMA-contraction pattern).
+DSAC_HDN DSAC_NOINLINE void p3p_front(const P3PProblem& pr, double f, double cx, double cy, P3PFront& fr) {
+    double inv_f = 1.0 / f, cx_f = cx * inv_f, cy_f = cy * inv_f;
     for (int i = 0; i < 3; i++) {
         double u = inv_f * pr.mu[i] - cx_f, v = inv_f * pr.mv[i] - cy_f;
+#if defined(__CUDA_ARCH__)
+        double k = rsqrt(u * u + v * v + 1);
+#else
         double k = 1. / sqrt(u * u + v * v + 1);
-        bear[i][0] = u * k; bear[i][1] = v * k; bear[i][2] = k;
+#endif
+        fr.bear[i][0] = u * k; fr.bear[i][1] = v * k; fr.bear[i][2] = k;
     }
-    double d12, d02, d01;
+    // only ratios of squared distances enter the quadrics; |AB| itself fixes the scale
+    double s12, s02, s01;
     {
         double dx = pr.X[1][0] - pr.X[2][0], dy = pr.X[1][1] - pr.X[2][1], dz = pr.X[1][2] - pr.X[2][2];
-        d12 = sqrt(dx * dx + dy * dy + dz * dz);
+        s12 = dx * dx + dy * dy + dz * dz;
         dx = pr.X[0][0] - pr.X[2][0]; dy = pr.X[0][1] - pr.X[2][1]; dz = pr.X[0][2] - pr.X[2][2];
-        d02 = sqrt(dx * dx + dy * dy + dz * dz);
+        s02 = dx * dx + dy * dy + dz * dz;
         dx = pr.X[0][0] - pr.X[1][0]; dy = pr.X[0][1] - pr.X[1][1]; dz = pr.X[0][2] - pr.X[1][2];
-        d01 = sqrt(dx * dx + dy * dy + dz * dz);
+        s01 = dx * dx + dy * dy + dz * dz;
     }
+    fr.d01 = sqrt(s01);
+    const double (*bear)[3] = fr.bear;
     double p = 2 * (bear[1][0] * bear[2][0] + bear[1][1] * bear[2][1] + bear[1][2] * bear[2][2]);
     double q = 2 * (bear[0][0] * bear[2][0] + bear[0][1] * bear[2][1] + bear[0][2] * bear[2][2]);
     double r = 2 * (bear[0][0] * bear[1][0] + bear[0][1] * bear[1][1] + bear[0][2] * bear[1][2]);
-    double inv_c2 = 1.0 / (d01 * d01);
-    double a = inv_c2 * d12 * d12, b = inv_c2 * d02 * d02;
-    if (p * p + q * q + r * r - p * q * r - 1 == 0) return 0;
-    // x = |PA|/|PC|, y = |PB|/|PC|:  y * Dn(x) = -Nn(x)
+    double inv_c2 = 1.0 / s01;
+    double a = inv_c2 * s12, b = inv_c2 * s02;
+    fr.p = p; fr.q = q; fr.r = r; fr.a = a; fr.b = b;
+    fr.nroots = 0;
+    if (p * p + q * q + r * r - p * q * r - 1 == 0) return;
     double N2 = 1 - a - b, N1 = q * (a - 1), N0 = 1 - a + b;
     double D1 = b * r, D0 = -b * p;
+    fr.N2 = N2; fr.N1 = N1; fr.N0 = N0; fr.D1 = D1; fr.D0 = D0;
     double c4, c3, c2, c1, c0;
     {
         double F2 = 1 - b, F1 = -q;
@@ -224,11 +247,42 @@ DSAC_HDN int p3p_best(const P3PProblem& pr, double f, double cx, double cy, doub
         c1 = F1 * DD0 + DD1 - b * (2 * N1 * N0) - br * (N0 * D0);
         c0 = DD0 - b * (N0 * N0);
     }
-    if (c4 == 0) return 0;
-    double xr[4];
-    int nroots = quartic_roots(c4, c3, c2, c1, c0, xr);
-    if (nroots == 0) return 0;
+    if (c4 == 0) return;
+    fr.nroots = quartic_roots(c4, c3, c2, c1, c0, fr.xr);
+}
 
+// y candidates for a quartic root x0: the linear relation, or (where it degenerates) both
+// roots of the first quadric.
+DSAC_HD int p3p_y_candidates(const P3PFront& fr, double x0, double* ya, double* yb) {
+    double Dn = fr.D1 * x0 + fr.D0;
+    if (fabs(Dn) > 1e-3 * (fabs(fr.D1 * x0) + fabs(fr.D0))) {
+        *ya = *yb = -((fr.N2 * x0 + fr.N1) * x0 + fr.N0) / Dn;
+        return 1;
+    }
+    double qa = 1 - fr.a, qb = fr.a * fr.r * x0 - fr.p, qc = 1 - fr.a * x0 * x0;
+    double disc = qb * qb - 4 * qa * qc;
+    if (disc < 0) disc = 0;
+    double sq = sqrt(disc);
+    if (qa != 0) {
+        *ya = (-qb + sq) / (2 * qa);
+        *yb = (-qb - sq) / (2 * qa);
+        return 2;
+    }
+    if (qb != 0) {
+        *ya = *yb = -qc / qb;
+        return 1;
+    }
+    *ya = *yb = 0;
+    return 0;
+}
+
+// All P3P solutions from points 0..2 (given the front end), the one with the smallest squared
+// reprojection error of point 3 is returned (cv::solvePnP CV_P3P semantics).  Returns the
+// number of solutions; *best_err2 is that smallest squared error (pixels^2).
+DSAC_HDN int p3p_full(const P3PProblem& pr, const P3PFront& fr, double f, double cx, double cy, double Rbest[9],
+                      double tbest[3], double* best_err2) {
+    if (fr.nroots == 0) return 0;
+    const double a = fr.a, b = fr.b, p = fr.p, q = fr.q, r = fr.r;
     double Ew[9], Cw[3];
     triangle_frame(pr.X[0], pr.X[1], pr.X[2], Ew);
     for (int k = 0; k < 3; k++) Cw[k] = (pr.X[0][k] + pr.X[1][k] + pr.X[2][k]) / 3;
@@ -236,33 +290,11 @@ DSAC_HDN int p3p_best(const P3PProblem& pr, double f, double cx, double cy, doub
     double sx[4], sy[4];
     int ns = 0, nsol = 0;
     double best = 0;
-    for (int i = 0; i < nroots; i++) {
-        double x0 = xr[i];
+    for (int i = 0; i < fr.nroots; i++) {
+        double x0 = fr.xr[i];
         if (!(x0 == x0)) continue;
-        double Dn = D1 * x0 + D0;
         double y0a, y0b;
-        int nc;
-        if (fabs(Dn) > 1e-3 * (fabs(D1 * x0) + fabs(D0))) {
-            y0a = -((N2 * x0 + N1) * x0 + N0) / Dn;
-            y0b = y0a;
-            nc = 1;
-        } else {  // both roots of the first quadric are candidates
-            double qa = 1 - a, qb = a * r * x0 - p, qc = 1 - a * x0 * x0;
-            double disc = qb * qb - 4 * qa * qc;
-            if (disc < 0) disc = 0;
-            double sq = sqrt(disc);
-            if (qa != 0) {
-                y0a = (-qb + sq) / (2 * qa);
-                y0b = (-qb - sq) / (2 * qa);
-                nc = 2;
-            } else if (qb != 0) {
-                y0a = y0b = -qc / qb;
-                nc = 1;
-            } else {
-                y0a = y0b = 0;
-                nc = 0;
-            }
-        }
+        int nc = p3p_y_candidates(fr, x0, &y0a, &y0b);
         for (int c = 0; c < nc; c++) {
             double x = x0, y = c ? y0b : y0a;
             bool good = false;
@@ -297,9 +329,9 @@ DSAC_HDN int p3p_best(const P3PProblem& pr, double f, double cx, double cy, doub
             ns++;
             double v = x * x + y * y - x * y * r;
             if (!(v > 0)) continue;
-            double Z = d01 / sqrt(v);
+            double Z = fr.d01 / sqrt(v);
             double R[9], t[3];
-            pose_from_lengths(x * Z, y * Z, Z, bear, Ew, Cw, R, t);
+            pose_from_lengths(x * Z, y * Z, Z, fr.bear, Ew, Cw, R, t);
             double X3 = R[0] * pr.X[3][0] + R[1] * pr.X[3][1] + R[2] * pr.X[3][2] + t[0];
             double Y3 = R[3] * pr.X[3][0] + R[4] * pr.X[3][1] + R[5] * pr.X[3][2] + t[1];
             double Z3 = R[6] * pr.X[3][0] + R[7] * pr.X[3][1] + R[8] * pr.X[3][2] + t[2];
@@ -317,6 +349,80 @@ DSAC_HDN int p3p_best(const P3PProblem& pr, double f, double cx, double cy, doub
     return nsol;
 }
 
+DSAC_HDN int p3p_best(const P3PProblem& pr, double f, double cx, double cy, double Rbest[9], double tbest[3],
+                      double* best_err2) {
+    P3PFront fr;
+    p3p_front(pr, f, cx, cy, fr);
+    return p3p_full(pr, fr, f, cx, cy, Rbest, tbest, best_err2);
+}
+
+// Conservative filter: returns false only if the full solve certainly cannot produce a pose
+// whose 4th-point error is below `thr` (so the candidate is certainly rejected by the
+// sampling loop, cnn_softam.h:1049-1057); returns true ("needs the full solve") otherwise,
+// including every numerically delicate situation.  Per root it takes ONE Newton step on the
+// two quadrics; if that step is tiny and well conditioned the stepped (x, y) is within ~1e-12
+// of the true solution, and the 4th point's camera position follows from the congruence of
+// the camera and world triangles without building the pose:
+//   M3 = M0 + alpha e1 + beta e2 + gamma e3,  e1 = (M1-M0)/d01, e3 = (M1-M0)x(M2-M0)/|n_w|, e2 = e3 x e1.
+DSAC_HDN bool p3p_quick_needs_full(const P3PProblem& pr, const P3PFront& fr, double f, double cx, double cy, double thr) {
+    if (fr.nroots == 0) return false;  // same front end as the full solve: it finds nothing either
+    const double a = fr.a, b = fr.b, p = fr.p, q = fr.q, r = fr.r;
+    // world triangle frame and the 4th point's coordinates in it
+    double ax = pr.X[1][0] - pr.X[0][0], ay = pr.X[1][1] - pr.X[0][1], az = pr.X[1][2] - pr.X[0][2];
+    double bx = pr.X[2][0] - pr.X[0][0], by = pr.X[2][1] - pr.X[0][1], bz = pr.X[2][2] - pr.X[0][2];
+    double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    double nn = nx * nx + ny * ny + nz * nz;
+    if (!(fr.d01 > 0) || !(nn > 0)) return true;
+    double inv_d = 1.0 / fr.d01, inv_n = 1.0 / sqrt(nn);
+    double e1x = ax * inv_d, e1y = ay * inv_d, e1z = az * inv_d;
+    double e3x = nx * inv_n, e3y = ny * inv_n, e3z = nz * inv_n;
+    double e2x = e3y * e1z - e3z * e1y, e2y = e3z * e1x - e3x * e1z, e2z = e3x * e1y - e3y * e1x;
+    double wx = pr.X[3][0] - pr.X[0][0], wy = pr.X[3][1] - pr.X[0][1], wz = pr.X[3][2] - pr.X[0][2];
+    double al = wx * e1x + wy * e1y + wz * e1z, be = wx * e2x + wy * e2y + wz * e2z, ga = wx * e3x + wy * e3y + wz * e3z;
+    const double lim2 = (thr + 1.0) * (thr + 1.0);
+    for (int i = 0; i < fr.nroots; i++) {
+        double x0 = fr.xr[i];
+        if (!(x0 == x0)) return true;
+        double y0a, y0b;
+        int nc = p3p_y_candidates(fr, x0, &y0a, &y0b);
+        if (nc != 1) return true;  // degenerate linear relation: let the full solve handle it
+        double x = x0, y = y0a;
+        double f1 = (1 - a) * y * y - a * x * x - p * y + a * r * x * y + 1;
+        double f2 = (1 - b) * x * x - b * y * y - q * x + b * r * x * y + 1;
+        double j11 = -2 * a * x + a * r * y, j12 = 2 * (1 - a) * y - p + a * r * x;
+        double j21 = 2 * (1 - b) * x - q + b * r * y, j22 = -2 * b * y + b * r * x;
+        double det = j11 * j22 - j12 * j21;
+        double jn = j11 * j11 + j12 * j12 + j21 * j21 + j22 * j22;
+        if (!(fabs(det) > 1e-4 * jn)) return true;  // (near-)singular Jacobian, NaN
+        double idet = 1.0 / det;
+        double dx = (f1 * j22 - f2 * j12) * idet, dy = (j11 * f2 - j21 * f1) * idet;
+        x -= dx;
+        y -= dy;
+        if (!(fabs(dx) + fabs(dy) <= 1e-6 * (fabs(x) + fabs(y)))) return true;  // not yet in the quadratic regime
+        if (x < -1e-6 || y < -1e-6) continue;       // certainly a non-physical solution
+        if (x < 1e-6 || y < 1e-6) return true;      // borderline positivity
+        double v = x * x + y * y - x * y * r;
+        if (!(v > 1e-12)) return true;
+        double Z = fr.d01 / sqrt(v);
+        double L0 = x * Z, L1 = y * Z;
+        double M0x = L0 * fr.bear[0][0], M0y = L0 * fr.bear[0][1], M0z = L0 * fr.bear[0][2];
+        double ux = L1 * fr.bear[1][0] - M0x, uy = L1 * fr.bear[1][1] - M0y, uz = L1 * fr.bear[1][2] - M0z;
+        double vx = Z * fr.bear[2][0] - M0x, vy = Z * fr.bear[2][1] - M0y, vz = Z * fr.bear[2][2] - M0z;
+        double cxn = uy * vz - uz * vy, cyn = uz * vx - ux * vz, czn = ux * vy - uy * vx;
+        double c1x = ux * inv_d, c1y = uy * inv_d, c1z = uz * inv_d;
+        double c3x = cxn * inv_n, c3y = cyn * inv_n, c3z = czn * inv_n;
+        double c2x = c3y * c1z - c3z * c1y, c2y = c3z * c1x - c3x * c1z, c2z = c3x * c1y - c3y * c1x;
+        double X3 = M0x + al * c1x + be * c2x + ga * c3x;
+        double Y3 = M0y + al * c1y + be * c2y + ga * c3y;
+        double Z3 = M0z + al * c1z + be * c2z + ga * c3z;
+        double iz = 1.0 / Z3;
+        double du = cx + f * X3 * iz - pr.mu[3], dv = cy + f * Y3 * iz - pr.mv[3];
+        double e2 = du * du + dv * dv;
+        if (!(e2 > lim2)) return true;  // possibly below the threshold (or NaN): full solve decides
+    }
+    return false;
+}
+
 // The pixel a P3P solve actually sees: cv::undistortPoints rounds the normalised
 // coordinate to float, p3p maps it back through K.
 DSAC_HD double p3p_pixel(float pix, double c, double f) {
@@ -328,18 +434,15 @@ DSAC_HD double p3p_pixel(float pix, double c, double f) {
 // P3P on the 4 correspondences, then all 4 reprojection errors (projection rounded to
 // float, float difference, double norm) must be below the integer threshold.
 // Returns true if accepted; rvec/tvec are the cv pose.  *fragile is set when a decision
-// was within 1e-6 px of the threshold.
-DSAC_HDN bool minimal_set_hypothesis(const float obj[12], const float img[8], double f, double cx, double cy, int thr,
-                                     double rvec[3], double tvec[3], bool* fragile) {
-    P3PProblem pr;
-    for (int i = 0; i < 4; i++) {
-        pr.mu[i] = p3p_pixel(img[i * 2], cx, f);
-        pr.mv[i] = p3p_pixel(img[i * 2 + 1], cy, f);
-        pr.X[i][0] = obj[i * 3]; pr.X[i][1] = obj[i * 3 + 1]; pr.X[i][2] = obj[i * 3 + 2];
-    }
+// was within 1e-6 px of the threshold.  pr: the P3P problem (see make_problem); obj/img: the
+// float correspondences the reprojection check uses.
+DSAC_HDN bool minimal_set_hypothesis_pr(const P3PProblem& pr, const float obj[12], const float img[8], double f, double cx,
+                                        double cy, int thr, double rvec[3], double tvec[3], bool* fragile) {
     double R[9], t[3], e2;
     *fragile = false;
-    if (p3p_best(pr, f, cx, cy, R, t, &e2) == 0) return false;
+    P3PFront fr;
+    p3p_front(pr, f, cx, cy, fr);
+    if (p3p_full(pr, fr, f, cx, cy, R, t, &e2) == 0) return false;
     // cheap exact-safe pre-check: the 4th point's error as P3P measured it differs from the
     // reference's float-rounded check by < 1e-4 px
     if (!(e2 < ((double)thr + 1e-3) * ((double)thr + 1e-3))) return false;
@@ -357,6 +460,205 @@ DSAC_HDN bool minimal_set_hypothesis(const float obj[12], const float img[8], do
         if (!(nrm < thr)) ok = false;
     }
     return ok;
+}
+
+DSAC_HD void make_problem(const float obj[12], const float img[8], double f, double cx, double cy, P3PProblem& pr) {
+    for (int i = 0; i < 4; i++) {
+        pr.mu[i] = p3p_pixel(img[i * 2], cx, f);
+        pr.mv[i] = p3p_pixel(img[i * 2 + 1], cy, f);
+        pr.X[i][0] = obj[i * 3]; pr.X[i][1] = obj[i * 3 + 1]; pr.X[i][2] = obj[i * 3 + 2];
+    }
+}
+
+DSAC_HDN bool minimal_set_hypothesis(const float obj[12], const float img[8], double f, double cx, double cy, int thr,
+                                     double rvec[3], double tvec[3], bool* fragile) {
+    P3PProblem pr;
+    make_problem(obj, img, f, cx, cy, pr);
+    return minimal_set_hypothesis_pr(pr, obj, img, f, cx, cy, thr, rvec, tvec, fragile);
+}
+
+// ---------------------------------------------------------------------------------------
+// fp32 version of the conservative filter.  Same decision contract as p3p_quick_needs_full
+// ("false" only if the candidate is certainly rejected), but every quantity whose rounding
+// could matter is guarded by a tolerance band three or more orders of magnitude wider than
+// fp32 rounding, and anything inside a band is handed to the fp64 full solve:
+//   * existence of real quartic roots (R^2, D^2, E^2 of Ferrari's method near zero),
+//   * the linear relation for y (denominator near zero),
+//   * Newton convergence / conditioning of the two-quadric system,
+//   * positivity of x, y, v,
+//   * the 4th point's error within 10 px of the threshold.
+// The quartic's coefficients are formed in double from the fp32 geometry (60 flops) so the
+// roots are those of a nearby well-posed problem; root finding and the per-root work are fp32.
+#if defined(__CUDA_ARCH__)
+#define DSAC_RSQRTF(x) rsqrtf(x)
+#else
+#define DSAC_RSQRTF(x) (1.0f / sqrtf(x))
+#endif
+
+DSAC_HD float cubic_first_root_f32(float a2, float a1, float a0) {
+    float Q = (3 * a1 - a2 * a2) * (1.f / 9);
+    float R = (9 * a2 * a1 - 27 * a0 - 2 * a2 * a2 * a2) * (1.f / 54);
+    float Q3 = Q * Q * Q, D = Q3 + R * R, sh = a2 * (1.f / 3);
+    float y;
+    if (D <= 0 && Q < 0) {
+        float c = R * DSAC_RSQRTF(-Q3);
+        c = fminf(1.f, fmaxf(-1.f, c));
+        y = 2 * sqrtf(-Q) * cosf(acosf(c) * (1.f / 3)) - sh;
+    } else {
+        float AD = cbrtf(fabsf(R) + sqrtf(fmaxf(D, 0.f)));
+        AD = (R >= 0) ? AD : -AD;
+        float BD = (AD == 0) ? 0 : -Q / AD;
+        y = AD + BD - sh;
+    }
+    // one Newton step on the cubic removes most of the closed form's rounding
+    float g = ((y + a2) * y + a1) * y + a0, gp = (3 * y + 2 * a2) * y + a1;
+    if (gp != 0) y -= g / gp;
+    return y;
+}
+
+// returns true if the candidate needs the fp64 full solve
+#define DSAC_F32_FLAG(code) { if (reason) *reason = (code); return true; }
+DSAC_HDN bool minimal_set_needs_full_f32(const float obj[12], const float img[8], double fd, double cxd, double cyd, int thr,
+                                        int* reason = nullptr) {
+    const float f = (float)fd, cx = (float)cxd, cy = (float)cyd, inv_f = 1.f / f;
+    float bear[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float u = (img[i * 2] - cx) * inv_f, v = (img[i * 2 + 1] - cy) * inv_f;
+        float k = DSAC_RSQRTF(u * u + v * v + 1);
+        bear[i][0] = u * k; bear[i][1] = v * k; bear[i][2] = k;
+    }
+    const float u3 = img[6], v3 = img[7];
+    float ax = obj[3] - obj[0], ay = obj[4] - obj[1], az = obj[5] - obj[2];      // X1 - X0
+    float bx = obj[6] - obj[0], by = obj[7] - obj[1], bz = obj[8] - obj[2];      // X2 - X0
+    float cxx = obj[6] - obj[3], cyy = obj[7] - obj[4], czz = obj[8] - obj[5];   // X2 - X1
+    float s01 = ax * ax + ay * ay + az * az, s02 = bx * bx + by * by + bz * bz, s12 = cxx * cxx + cyy * cyy + czz * czz;
+    float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    float nn = nx * nx + ny * ny + nz * nz;
+    if (!(s01 > 0) || !(nn > 1e-6f * s01 * s02)) DSAC_F32_FLAG(1)   // degenerate / nearly collinear triangle
+    float inv01 = 1.f / s01;
+    float af = s12 * inv01, bf = s02 * inv01;
+    float pf = 2 * (bear[1][0] * bear[2][0] + bear[1][1] * bear[2][1] + bear[1][2] * bear[2][2]);
+    float qf = 2 * (bear[0][0] * bear[2][0] + bear[0][1] * bear[2][1] + bear[0][2] * bear[2][2]);
+    float rf = 2 * (bear[0][0] * bear[1][0] + bear[0][1] * bear[1][1] + bear[0][2] * bear[1][2]);
+    float N2f, N1f, N0f, D1f, D0f, shift, P, Q, Rr;
+    {
+        double a = af, b = bf, p = pf, q = qf, r = rf;
+        double N2 = 1 - a - b, N1 = q * (a - 1), N0 = 1 - a + b, D1 = b * r, D0 = -b * p;
+        double F2 = 1 - b, F1 = -q;
+        double DD2 = D1 * D1, DD1 = 2 * D1 * D0, DD0 = D0 * D0, br = b * r;
+        double c4 = F2 * DD2 - b * (N2 * N2) - br * (N2 * D1);
+        double c3 = F2 * DD1 + F1 * DD2 - b * (2 * N2 * N1) - br * (N2 * D0 + N1 * D1);
+        double c2 = F2 * DD0 + F1 * DD1 + DD2 - b * (2 * N2 * N0 + N1 * N1) - br * (N1 * D0 + N0 * D1);
+        double c1 = F1 * DD0 + DD1 - b * (2 * N1 * N0) - br * (N0 * D0);
+        double c0 = DD0 - b * (N0 * N0);
+        double sc = fabs(c4) + fabs(c3) + fabs(c2) + fabs(c1) + fabs(c0);
+        if (!(fabs(c4) > 1e-6 * sc)) DSAC_F32_FLAG(2)   // leading coefficient (nearly) vanishes
+        double i4 = 1.0 / c4;
+        double B = c3 * i4, C = c2 * i4, D = c1 * i4, E = c0 * i4;
+        // depressed quartic z^4 + P z^2 + Q z + Rr = 0, x = z - B/4: the roots cluster (x ~ 1), so the
+        // shift is done in double and the fp32 root finder only sees the spread
+        double B2 = B * B;
+        shift = (float)(0.25 * B);
+        P = (float)(C - 0.375 * B2);
+        Q = (float)(D - 0.5 * B * C + 0.125 * B2 * B);
+        Rr = (float)(E - 0.25 * B * D + 0.0625 * B2 * C - (3.0 / 256.0) * B2 * B2);
+        N2f = (float)N2; N1f = (float)N1; N0f = (float)N0; D1f = (float)D1; D0f = (float)D0;
+    }
+    // ---- Ferrari on the depressed quartic in fp32, with a tolerance band on every sign decision.
+    // scale of z: the bands are relative to it
+    const float TOL = 4e-3f;
+    float y1 = cubic_first_root_f32(-P, -4 * Rr, 4 * P * Rr - Q * Q);
+    if (!(y1 == y1)) DSAC_F32_FLAG(3)
+    float R2 = y1 - P, mR = fabsf(y1) + fabsf(P);
+    if (R2 < -TOL * mR) return false;               // certainly no real roots
+    if (!(R2 > TOL * mR)) DSAC_F32_FLAG(4)              // too close to call (includes the R ~ 0 branch)
+    float R = sqrtf(R2);
+    float uu = -2 * P - R2, vv = -2 * Q / R;
+    float mD = 2 * fabsf(P) + R2 + fabsf(vv);
+    float D2 = uu + vv, E2 = uu - vv;
+    float xr[4];
+    int n = 0;
+    if (D2 > TOL * mD) {
+        float Dq = sqrtf(D2);
+        xr[0] = 0.5f * R + 0.5f * Dq - shift;
+        xr[1] = xr[0] - Dq;
+        n = 2;
+    } else if (!(D2 < -TOL * mD)) DSAC_F32_FLAG(5)
+    if (E2 > TOL * mD) {
+        float Eq = sqrtf(E2);
+        xr[n] = -0.5f * R + 0.5f * Eq - shift;
+        xr[n + 1] = xr[n] - Eq;
+        n += 2;
+    } else if (!(E2 < -TOL * mD)) DSAC_F32_FLAG(6)
+    if (n == 0) return false;
+
+    // world frame and the 4th point's coordinates in it
+    float inv_d = DSAC_RSQRTF(s01), inv_n = DSAC_RSQRTF(nn), d01 = s01 * inv_d;
+    float e1x = ax * inv_d, e1y = ay * inv_d, e1z = az * inv_d;
+    float e3x = nx * inv_n, e3y = ny * inv_n, e3z = nz * inv_n;
+    float e2x = e3y * e1z - e3z * e1y, e2y = e3z * e1x - e3x * e1z, e2z = e3x * e1y - e3y * e1x;
+    float wx = obj[9] - obj[0], wy = obj[10] - obj[1], wz = obj[11] - obj[2];
+    float al = wx * e1x + wy * e1y + wz * e1z, be = wx * e2x + wy * e2y + wz * e2z, ga = wx * e3x + wy * e3y + wz * e3z;
+    const float lim2 = ((float)thr + 10.f) * ((float)thr + 10.f);
+    for (int i = 0; i < 4; i++) {
+        if (i >= n) break;
+        float x = xr[i];
+        float Dn = D1f * x + D0f;
+        if (!(fabsf(Dn) > 3e-2f * (fabsf(D1f * x) + fabsf(D0f)))) DSAC_F32_FLAG(7)
+        float y = -((N2f * x + N1f) * x + N0f) / Dn;
+        float dlast = 0;
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            float f1 = (1 - af) * y * y - af * x * x - pf * y + af * rf * x * y + 1;
+            float f2 = (1 - bf) * x * x - bf * y * y - qf * x + bf * rf * x * y + 1;
+            float j11 = -2 * af * x + af * rf * y, j12 = 2 * (1 - af) * y - pf + af * rf * x;
+            float j21 = 2 * (1 - bf) * x - qf + bf * rf * y, j22 = -2 * bf * y + bf * rf * x;
+            float det = j11 * j22 - j12 * j21;
+            float jn = j11 * j11 + j12 * j12 + j21 * j21 + j22 * j22;
+            if (!(fabsf(det) > 1e-2f * jn)) DSAC_F32_FLAG(8)
+            float idet = 1.f / det;
+            float dx = (f1 * j22 - f2 * j12) * idet, dy = (j11 * f2 - j21 * f1) * idet;
+            x -= dx;
+            y -= dy;
+            dlast = fabsf(dx) + fabsf(dy);
+        }
+        if (!(dlast <= 1e-3f * (fabsf(x) + fabsf(y)))) DSAC_F32_FLAG(9)
+        if (x < -1e-2f || y < -1e-2f) continue;     // certainly non-physical
+        if (x < 1e-2f || y < 1e-2f) DSAC_F32_FLAG(10)
+        float v = x * x + y * y - x * y * rf;
+        if (!(v > 1e-4f * (x * x + y * y))) DSAC_F32_FLAG(11)
+        float Z = d01 * DSAC_RSQRTF(v);
+        float L0 = x * Z, L1 = y * Z;
+        float M0x = L0 * bear[0][0], M0y = L0 * bear[0][1], M0z = L0 * bear[0][2];
+        float ux = L1 * bear[1][0] - M0x, uy = L1 * bear[1][1] - M0y, uz = L1 * bear[1][2] - M0z;
+        float vx = Z * bear[2][0] - M0x, vy = Z * bear[2][1] - M0y, vz = Z * bear[2][2] - M0z;
+        float cxn = uy * vz - uz * vy, cyn = uz * vx - ux * vz, czn = ux * vy - uy * vx;
+        float c1x = ux * inv_d, c1y = uy * inv_d, c1z = uz * inv_d;
+        float c3x = cxn * inv_n, c3y = cyn * inv_n, c3z = czn * inv_n;
+        float c2x = c3y * c1z - c3z * c1y, c2y = c3z * c1x - c3x * c1z, c2z = c3x * c1y - c3y * c1x;
+        float X3 = M0x + al * c1x + be * c2x + ga * c3x;
+        float Y3 = M0y + al * c1y + be * c2y + ga * c3y;
+        float Z3 = M0z + al * c1z + be * c2z + ga * c3z;
+        if (!(fabsf(Z3) > 1e-3f * (fabsf(X3) + fabsf(Y3) + 1.f))) DSAC_F32_FLAG(12)  // grazing projection
+        float iz = 1.f / Z3;
+        float du = cx + f * X3 * iz - u3, dv = cy + f * Y3 * iz - v3;
+        float e2 = du * du + dv * dv;
+        if (!(e2 > lim2)) DSAC_F32_FLAG(13)
+    }
+    return false;
+}
+
+// Quick conservative pre-test of a minimal set (see p3p_quick_needs_full).
+DSAC_HDN bool minimal_set_needs_full_pr(const P3PProblem& pr, double f, double cx, double cy, int thr) {
+    P3PFront fr;
+    p3p_front(pr, f, cx, cy, fr);
+    return p3p_quick_needs_full(pr, fr, f, cx, cy, (double)thr);
+}
+DSAC_HDN bool minimal_set_needs_full(const float obj[12], const float img[8], double f, double cx, double cy, int thr) {
+    P3PProblem pr;
+    make_problem(obj, img, f, cx, cy, pr);
+    return minimal_set_needs_full_pr(pr, f, cx, cy, thr);
 }
 
 }  // namespace dsac

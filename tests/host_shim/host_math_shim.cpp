@@ -56,3 +56,50 @@ void shim_candidates(uint32_t seed, uint32_t skip, int n, int32_t* cells, uint32
 }
 void shim_stream_chunk(int H, int T, int s, int* h0, int* cnt) { dsac::stream_chunk(H, T, s, h0, cnt); }
 }
+extern "C" int shim_needs_full(const float* obj, const float* img, double f, double cx, double cy, int thr) {
+    return dsac::minimal_set_needs_full(obj, img, f, cx, cy, thr) ? 1 : 0;
+}
+
+#include <random>
+static long long* g_reasons = nullptr; static int g_miss[64]; static int g_nmiss = 0;
+extern "C" void shim_set_reasons(long long* r) { g_reasons = r; }
+extern "C" int shim_get_misses(int* out) { for (int i = 0; i < g_nmiss * 4; i++) out[i] = g_miss[i]; int n = g_nmiss; g_nmiss = 0; return n; }
+// Filter statistics over the first n candidates of one frame's stream: how many candidates each
+// conservative filter hands to the full solve, and (the contract) how many ACCEPTED candidates a
+// filter would have dropped -- must be zero.
+extern "C" void shim_filter_stats(const int16_t* coords, const int32_t* pix, uint32_t seed, uint32_t skip, int n,
+                                  double f, double cx, double cy, int thr, long long out[6]) {
+    size_t words = (size_t)skip + (size_t)n * 10 + 4096;
+    size_t cap = 1;
+    while (cap < words) cap <<= 1;
+    std::vector<uint32_t> buf(cap);
+    shim_mt_raw(seed, (int)words, buf.data());
+    dsac::WordRing ring{buf.data(), (uint32_t)(cap - 1)};
+    uint32_t pos = skip;
+    for (int k = 0; k < 6; k++) out[k] = 0;
+    for (int k = 0; k < n; k++) {
+        int c[4];
+        uint32_t u = dsac::parse_candidate(ring, pos, (uint32_t)words, c);
+        pos += u;
+        float obj[12], img[8];
+        for (int j = 0; j < 4; j++) {
+            img[j * 2] = (float)pix[c[j] * 2];
+            img[j * 2 + 1] = (float)pix[c[j] * 2 + 1];
+            for (int q = 0; q < 3; q++) obj[j * 3 + q] = (float)coords[c[j] * 3 + q];
+        }
+        double rv[3], tv[3];
+        bool fr;
+        bool acc = dsac::minimal_set_hypothesis(obj, img, f, cx, cy, thr, rv, tv, &fr);
+        bool q64 = dsac::minimal_set_needs_full(obj, img, f, cx, cy, thr);
+        int reason = 0;
+        bool q32 = dsac::minimal_set_needs_full_f32(obj, img, f, cx, cy, thr, &reason);
+        if (q32 && g_reasons) g_reasons[reason]++;
+        if (acc && !q32 && g_nmiss < 16) { for (int j = 0; j < 4; j++) g_miss[g_nmiss * 4 + j] = c[j]; g_nmiss++; }
+        out[0]++;
+        out[1] += acc;
+        out[2] += q64;
+        out[3] += q32;
+        out[4] += (acc && !q64);
+        out[5] += (acc && !q32);
+    }
+}
