@@ -228,11 +228,11 @@ __global__ void __launch_bounds__(K4_THREADS) k_refine(RefineParams p) {
     __shared__ double s_red[K4_WARPS][28];
     __shared__ double s_sum[28];
     __shared__ int s_scan[K4_WARPS];
-    __shared__ int s_flag;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int job = blockIdx.x;
     const int frame = p.job_frame ? p.job_frame[job] : job;
+    if (frame < 0) return;  // unused job slot
     const int16_t* coords = p.coords + (size_t)frame * DSAC_N_CONST * 3;
     const int32_t* pix = p.pix + (size_t)frame * p.pix_stride;
     int pert_idx = -1, pert_delta = 0;
