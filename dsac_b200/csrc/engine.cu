@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <random>
@@ -50,6 +51,7 @@ struct dsac_engine {
     long long* d_stream_ncand = nullptr;
     uint32_t* d_status = nullptr;
     unsigned long long* d_fragile = nullptr;
+    unsigned long long* d_phase = nullptr;   // K1 per-phase cycle counters (DSAC_K1_TIMERS=1), else null
     float* d_diffmaps = nullptr;
     double* d_scores = nullptr;
     double* d_sf = nullptr;
@@ -125,6 +127,12 @@ int dsac_engine_config(const dsac_engine* e, dsac_config* out) {
 void dsac_engine_destroy(dsac_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    if (e->d_phase) {
+        unsigned long long h[16];
+        if (cudaMemcpy(h, e->d_phase, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+            fprintf(stderr, "[dsac K1 thread-0 cycles] A1 gen %llu  A2 bounds %llu  B filter %llu  C queue %llu  D full %llu  E advance %llu\n", h[0], h[1], h[2], h[3], h[4], h[5]);
+        cudaFree(e->d_phase);
+    }
     void* ptrs[] = {e->d_coords, e->d_pix, e->d_gt, e->d_perm, e->d_hyp_pose, e->d_hyp_P, e->d_img_idx, e->d_cand_idx,
                     e->d_stream_ncand, e->d_status, e->d_fragile, e->d_diffmaps, e->d_scores, e->d_sf, e->d_entropy,
                     e->d_avg, e->d_ref, e->d_inlier_map, e->d_steps_done, e->d_n_perm, e->d_loss, e->d_rot_err,
@@ -198,6 +206,10 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
     CUC(cudaMalloc(&e->d_frame_counter, n * sizeof(unsigned int)));
     CUC(cudaMemset(e->d_frame_counter, 0, n * sizeof(unsigned int)));
     CUC(cudaMemset(e->d_fragile, 0, sizeof(unsigned long long)));
+    if (getenv("DSAC_K1_TIMERS")) {
+        CUC(cudaMalloc(&e->d_phase, 16 * sizeof(unsigned long long)));
+        CUC(cudaMemset(e->d_phase, 0, 16 * sizeof(unsigned long long)));
+    }
     CUC(cudaMemset(e->d_status, 0, n * sizeof(uint32_t)));
     CUC(cudaMemset(e->d_steps_done, 0, n * sizeof(int32_t)));
     CUC(cudaMemset(e->d_n_perm, 0, n * sizeof(int32_t)));
@@ -281,6 +293,7 @@ int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
         sp.frame0 = frame0;
         sp.hyp_pose = e->d_hyp_pose; sp.hyp_P = e->d_hyp_P; sp.img_idx = e->d_img_idx; sp.cand_idx = e->d_cand_idx;
         sp.stream_ncand = e->d_stream_ncand; sp.status = e->d_status; sp.n_fragile = e->d_fragile;
+        sp.phase_cycles = e->d_phase;
         k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);
         e->launches++;
         CU(cudaGetLastError());

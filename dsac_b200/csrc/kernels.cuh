@@ -57,6 +57,7 @@ struct SampleParams {
     long long* stream_ncand; // [n][T]
     uint32_t* status;        // [n]
     unsigned long long* n_fragile;  // [1]
+    unsigned long long* phase_cycles;  // [8] or null: thread-0 cycles per phase (development aid)
 };
 
 constexpr int K1_THREADS = 256;
@@ -67,7 +68,6 @@ constexpr int K1_SUPER_MAX = 16;                          // x256 candidates per
 constexpr int K1_CANDS = K1_SUPER_MAX * K1_THREADS;       // candidates buffered per super-round
 constexpr int K1_WORDS = K1_CANDS * 8 + 1024;             // decoded stream words buffered per super-round
 constexpr int K1_WAVE = MT_N - MT_M;                      // 227 new MT19937 words per barrier
-constexpr int K1_SEGS = 32, K1_WALK = 8;                  // chain walkers: 32 segments x 8 entry offsets
 
 // Per-cell record staged in shared memory: scene coordinate (mm) and the float-rounded
 // normalised pixel that cv::undistortPoints hands to P3P.
@@ -80,16 +80,12 @@ struct K1Smem {
     CellRec cell[DSAC_N_CONST];
     uint32_t st[1024];                          // sliding window of the raw MT19937 sequence (linear index & 1023)
     __align__(4) unsigned char vals[K1_WORDS];  // Lemire value (0..39) of stream word pos+i; 255 = rejected draw
-    unsigned char elen[K1_WORDS / 2];           // words consumed by a candidate starting at even offset 2i (0 = does not fit)
     unsigned short cand_start[K1_CANDS + 512];    // word offset (from pos) where candidate i starts
     unsigned short q_idx[K1_CANDS];             // queue of candidates that need the full solve, ascending
     uint32_t flagbits[K1_CANDS / 32];
     uint32_t wordbase[K1_CANDS / 32];
-    unsigned short wk_exit[K1_SEGS * K1_WALK];
-    unsigned short wk_cnt[K1_SEGS * K1_WALK];
-    unsigned short seg_base[K1_SEGS + 1];
-    unsigned char seg_sel[K1_SEGS];
     int warp[2][8];
+    uint32_t newpos;
     int q_n, n_sr, any_reject, walk_fail;
 };
 
@@ -138,7 +134,7 @@ __device__ __forceinline__ int cand_parse_fast(const unsigned char* vals, int q,
 
 // One CTA per (frame, stream).  Per super-round of up to S x 256 candidates:
 //   A  MT19937 in waves of 227 words (one barrier each), every word decoded on the fly to its
-//      uniform_int_distribution value; candidate boundaries by 256 speculative chain walkers
+//      uniform_int_distribution value; candidate boundaries by a block-wide fixed point over per-thread runs
 //   B  cheap conservative filter, one thread per candidate, no block barriers
 //   C  queue the ~2% that need the full fp64 P3P, in candidate order
 //   D  full solve + reprojection check on the queue, ordered compaction of the accepted
@@ -190,6 +186,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
         }
     };
 
+    long long tA1 = 0, tA2 = 0, tB = 0, tC = 0, tD = 0, tE = 0, tmark = clock64();
+#define K1_MARK(var) do { long long _n = clock64(); var += _n - tmark; tmark = _n; } while (0)
     while (acc < quota && cand_base < cand_max) {
         // ---------------- phase A1: generate + decode words until the super-round's window is full
         long long want = (long long)S * K1_THREADS;
@@ -214,77 +212,56 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
             __syncthreads();
         }
         const int w_avail = min((int)(gen - pos), K1_WORDS);
+        K1_MARK(tA1);
 
         // ---------------- phase A2: candidate boundaries.  A candidate is 8 words long unless a cell repeats
-        // (+2 words) or a draw is rejected (+1).  (i) every even offset gets the length of the candidate that
-        // would start there; (ii) thread (m, c) follows the chain through segment m assuming it enters at
-        // offset 2c; (iii) the true chain is stitched from the matching walkers and written out.
-        for (int i = tid * 2; i < w_avail; i += K1_THREADS * 2) {
-            int cells[4];
-            int qn = cand_parse_fast(sm.vals, i, w_avail, cells);
-            sm.elen[i >> 1] = (qn < 0) ? (unsigned char)0 : (unsigned char)(qn - i);
-        }
-        __syncthreads();
-        const int seg_len = ((w_need / K1_SEGS) + 7) & ~7;
+        // (+2 words) or a draw is rejected (+1).  Per chunk of 256 candidates (one per thread), the starts
+        // 8*tid + (extra words of earlier candidates) are iterated to a fixed point -- one pass when the chunk
+        // has no repeat (39 %), else typically 2-3 cheap passes; at the fixed point candidate 0 is exact,
+        // hence candidate 1, and so on.
         {
-            const int m = tid / K1_WALK, c = tid % K1_WALK;
-            int q = m * seg_len + 2 * c, cnt = 0;
-            const int seg_end = min((m + 1) * seg_len, w_avail);
-            while (q < seg_end) {
-                int l = sm.elen[q >> 1];
-                if (l == 0 || (l & 1)) break;   // window exhausted / odd length: only the sequential path handles it
-                q += l;
-                cnt++;
-            }
-            sm.wk_exit[tid] = (unsigned short)q;   // first chain position >= seg_end (or where the words ran out)
-            sm.wk_cnt[tid] = (unsigned short)cnt;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int q = 0, total = 0;
-            bool fail = sm.any_reject != 0;
-            for (int m = 0; m < K1_SEGS && !fail; m++) {
-                sm.seg_base[m] = (unsigned short)total;
-                int off = q - m * seg_len;
-                if (off < 0 || q >= min((m + 1) * seg_len, w_avail)) { sm.seg_sel[m] = 255; continue; }  // chain ended earlier
-                if ((off & 1) || off >= 2 * K1_WALK) { fail = true; break; }
-                sm.seg_sel[m] = (unsigned char)(off >> 1);
-                total += sm.wk_cnt[m * K1_WALK + (off >> 1)];
-                q = sm.wk_exit[m * K1_WALK + (off >> 1)];
-            }
-            sm.seg_base[K1_SEGS] = (unsigned short)total;
-            if (fail) {  // rejected draw in the window (p ~ 1e-4 per super-round) or >7 repeats: plain sequential walk
-                q = 0; total = 0;
-                while (total < K1_CANDS + 500) {
+            int rp = 0, n_done = 0, par = 0;   // word offset of the chunk, candidates placed so far
+            bool out_of_words = false;
+            while (n_done < n_target && !out_of_words) {
+                const int n_chunk = min(K1_THREADS, n_target - n_done);
+                int extra = 0, start = 0, qn = 0;
+                for (;;) {
+                    int tot;
+                    const int excl = block_excl_scan_256(extra, &tot, sm.warp[par]);
+                    par ^= 1;
+                    start = rp + 8 * tid + excl;
                     int cells[4];
-                    int qn = cand_parse(sm.vals, q, w_avail, cells);
-                    if (qn < 0) break;
-                    sm.cand_start[total++] = (unsigned short)q;
-                    q = qn;
+                    qn = (tid < n_chunk) ? cand_parse_fast(sm.vals, start, w_avail, cells) : start + 8;
+                    const int ne = (qn < 0) ? 0 : (qn - start) - 8;
+                    const int changed = (ne != extra);
+                    extra = ne;
+                    if (!__syncthreads_or(changed)) break;
                 }
-                sm.cand_start[total] = (unsigned short)q;
-                sm.walk_fail = 1;
+                // (practically never) the buffered words ran out inside this chunk: keep the complete prefix
+                int bad = (tid < n_chunk && qn < 0) ? tid : K1_THREADS;
+#pragma unroll
+                for (int off = 16; off; off >>= 1) bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, off));
+                if (lane == 0) sm.warp[par][tid >> 5] = bad;
+                __syncthreads();
+                int n_ok = n_chunk;
+#pragma unroll
+                for (int w = 0; w < 8; w++) n_ok = min(n_ok, sm.warp[par][w]);
+                par ^= 1;
+                if (tid < n_ok) sm.cand_start[n_done + tid] = (unsigned short)start;
+                if (tid == n_ok - 1) sm.newpos = (uint32_t)qn;          // end of the last complete candidate
+                __syncthreads();
+                if (n_ok > 0) rp = (int)sm.newpos;
+                n_done += n_ok;
+                out_of_words = (n_ok < n_chunk);
             }
-            sm.n_sr = min(total, n_target);
-        }
-        __syncthreads();
-        if (!sm.walk_fail && (tid % K1_WALK) == 0) {   // re-walk the selected chains and record the starts
-            const int m = tid / K1_WALK;
-            const int sel = sm.seg_sel[m];
-            if (sel != 255) {
-                int q = m * seg_len + 2 * sel, idx = sm.seg_base[m];
-                const int seg_end = min((m + 1) * seg_len, w_avail);
-                while (q < seg_end) {
-                    int l = sm.elen[q >> 1];
-                    if (l == 0) break;
-                    sm.cand_start[idx++] = (unsigned short)q;
-                    q += l;
-                }
-                if (idx == sm.seg_base[K1_SEGS]) sm.cand_start[idx] = (unsigned short)q;  // end of the last candidate
+            if (tid == 0) {
+                sm.cand_start[n_done] = (unsigned short)rp;
+                sm.n_sr = n_done;
             }
         }
         __syncthreads();
         const int n_sr = sm.n_sr;
+        K1_MARK(tA2);
 
         // ---------------- phase B: conservative filter, warps run without block barriers
         for (int i0 = 0; i0 < n_sr; i0 += K1_THREADS) {
@@ -302,6 +279,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
         }
         __syncthreads();
 
+        K1_MARK(tB);
         // ---------------- phase C: queue of flagged candidates in candidate order
         const int n_words = (n_sr + 31) >> 5;   // <= 128
         if (tid < 32) {
@@ -335,6 +313,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
         }
         __syncthreads();
         const int q_n = sm.q_n;
+        K1_MARK(tC);
 
         // ---------------- phase D: full fp64 P3P + reprojection check (cnn_softam.h:1041-1059) on the
         //                  queue, then the first `quota` accepted candidates of the stream, in order
@@ -381,6 +360,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
             acc += tot;
         }
 
+        K1_MARK(tD);
         // ---------------- advance the stream: the unread tail of the window moves to the front
         {
             const int consumed = sm.cand_start[n_sr];
@@ -417,6 +397,12 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
             }
         }
         __syncthreads();
+        K1_MARK(tE);
+    }
+    if (p.phase_cycles && tid == 0) {
+        atomicAdd(p.phase_cycles + 0, (unsigned long long)tA1); atomicAdd(p.phase_cycles + 1, (unsigned long long)tA2);
+        atomicAdd(p.phase_cycles + 2, (unsigned long long)tB); atomicAdd(p.phase_cycles + 3, (unsigned long long)tC);
+        atomicAdd(p.phase_cycles + 4, (unsigned long long)tD); atomicAdd(p.phase_cycles + 5, (unsigned long long)tE);
     }
 
     if (acc < quota) {  // sampler exhausted: value-encode like a failed PnP (zero pose, cnn_softam.h:66-71)

@@ -147,6 +147,47 @@ DSAC_HD int quartic_roots(double a, double b, double c, double d, double e, doub
     return n;
 }
 
+DSAC_HD double rsqrt_or(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// quartic_roots with an "uncertain" verdict: set when any sign decision of Ferrari's method lies
+// within a relative band of 1e-9 (>= 10^6 x double rounding), i.e. when another instance of the same
+// computation with different rounding could decide differently.  Used by the conservative filter.
+DSAC_HD int quartic_roots_banded(double a, double b, double c, double d, double e, double x[4], bool* uncertain) {
+    const double TOL = 1e-9;
+    *uncertain = false;
+    double ia = 1.0 / a;
+    b *= ia; c *= ia; d *= ia; e *= ia;
+    double y1 = cubic_first_root(-c, d * b - 4 * e, 4 * c * e - d * d - b * b * e);
+    double R2 = 0.25 * b * b - c + y1, mR = 0.25 * b * b + fabs(c) + fabs(y1);
+    if (!(fabs(R2) > TOL * mR)) { *uncertain = true; return 0; }   // also catches NaN and the R ~ 0 branch
+    if (R2 < 0) return 0;
+    double R = sqrt(R2);
+    double u = 0.75 * b * b - 2 * c - R2;
+    double v = 0.25 * (4 * b * c - 8 * d - b * b * b) / R;
+    double D2 = u + v, E2 = u - v, mD = fabs(0.75 * b * b) + fabs(2 * c) + R2 + fabs(v);
+    if (!(fabs(D2) > TOL * mD) || !(fabs(E2) > TOL * mD)) { *uncertain = true; return 0; }
+    int n = 0;
+    if (D2 > 0) {
+        double Dq = sqrt(D2);
+        x[0] = 0.5 * R + 0.5 * Dq - 0.25 * b;
+        x[1] = x[0] - Dq;
+        n = 2;
+    }
+    if (E2 > 0) {
+        double Eq = sqrt(E2);
+        x[n] = -0.5 * R + 0.5 * Eq - 0.25 * b;
+        x[n + 1] = x[n] - Eq;
+        n += 2;
+    }
+    return n;
+}
+
 struct P3PProblem {
     double mu[4], mv[4];  // pixel positions as P3P sees them (float-rounded normalised coords mapped back through K)
     double X[4][3];       // scene coordinates (mm)
@@ -477,6 +518,103 @@ DSAC_HDN bool minimal_set_hypothesis(const float obj[12], const float img[8], do
     return minimal_set_hypothesis_pr(pr, obj, img, f, cx, cy, thr, rvec, tvec, fragile);
 }
 
+// Self-contained (fully inlined, register-resident) version of the conservative filter: same contract as
+// p3p_quick_needs_full, but it does not share the front end with the full solve, so every decision the
+// front end takes (degeneracy tests, existence of real roots) is protected by a tolerance band instead.
+DSAC_HD bool p3p_quick_inline(const P3PProblem& pr, double f, double cx, double cy, double inv_f, double thr) {
+    const double cx_f = cx * inv_f, cy_f = cy * inv_f;
+    double bear[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double u = inv_f * pr.mu[i] - cx_f, v = inv_f * pr.mv[i] - cy_f;
+#if defined(__CUDA_ARCH__)
+        double k = rsqrt(u * u + v * v + 1);
+#else
+        double k = 1. / sqrt(u * u + v * v + 1);
+#endif
+        bear[i][0] = u * k; bear[i][1] = v * k; bear[i][2] = k;
+    }
+    const double ax = pr.X[1][0] - pr.X[0][0], ay = pr.X[1][1] - pr.X[0][1], az = pr.X[1][2] - pr.X[0][2];
+    const double bx = pr.X[2][0] - pr.X[0][0], by = pr.X[2][1] - pr.X[0][1], bz = pr.X[2][2] - pr.X[0][2];
+    const double gx = pr.X[2][0] - pr.X[1][0], gy = pr.X[2][1] - pr.X[1][1], gz = pr.X[2][2] - pr.X[1][2];
+    const double s01 = ax * ax + ay * ay + az * az, s02 = bx * bx + by * by + bz * bz, s12 = gx * gx + gy * gy + gz * gz;
+    const double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    const double nn = nx * nx + ny * ny + nz * nz;
+    if (!(s01 > 0) || !(nn > 0)) return true;
+    const double p = 2 * (bear[1][0] * bear[2][0] + bear[1][1] * bear[2][1] + bear[1][2] * bear[2][2]);
+    const double q = 2 * (bear[0][0] * bear[2][0] + bear[0][1] * bear[2][1] + bear[0][2] * bear[2][2]);
+    const double r = 2 * (bear[0][0] * bear[1][0] + bear[0][1] * bear[1][1] + bear[0][2] * bear[1][2]);
+    const double inv_c2 = 1.0 / s01;
+    const double a = inv_c2 * s12, b = inv_c2 * s02;
+    if (!(fabs(p * p + q * q + r * r - p * q * r - 1) > 1e-12)) return true;
+    const double N2 = 1 - a - b, N1 = q * (a - 1), N0 = 1 - a + b;
+    const double D1 = b * r, D0 = -b * p;
+    double xr[4];
+    int nroots;
+    {
+        const double F2 = 1 - b, F1 = -q;
+        const double DD2 = D1 * D1, DD1 = 2 * D1 * D0, DD0 = D0 * D0, br = b * r;
+        const double c4 = F2 * DD2 - b * (N2 * N2) - br * (N2 * D1);
+        const double c3 = F2 * DD1 + F1 * DD2 - b * (2 * N2 * N1) - br * (N2 * D0 + N1 * D1);
+        const double c2 = F2 * DD0 + F1 * DD1 + DD2 - b * (2 * N2 * N0 + N1 * N1) - br * (N1 * D0 + N0 * D1);
+        const double c1 = F1 * DD0 + DD1 - b * (2 * N1 * N0) - br * (N0 * D0);
+        const double c0 = DD0 - b * (N0 * N0);
+        if (!(fabs(c4) > 1e-12 * (fabs(c3) + fabs(c2) + fabs(c1) + fabs(c0)))) return true;
+        bool uncertain;
+        nroots = quartic_roots_banded(c4, c3, c2, c1, c0, xr, &uncertain);
+        if (uncertain) return true;
+    }
+    if (nroots == 0) return false;   // no real root, by a margin no rounding can bridge
+    // world triangle frame and the 4th point's coordinates in it
+    const double inv_d = rsqrt_or(s01), inv_n = rsqrt_or(nn), d01 = s01 * inv_d;
+    const double e1x = ax * inv_d, e1y = ay * inv_d, e1z = az * inv_d;
+    const double e3x = nx * inv_n, e3y = ny * inv_n, e3z = nz * inv_n;
+    const double e2x = e3y * e1z - e3z * e1y, e2y = e3z * e1x - e3x * e1z, e2z = e3x * e1y - e3y * e1x;
+    const double wx = pr.X[3][0] - pr.X[0][0], wy = pr.X[3][1] - pr.X[0][1], wz = pr.X[3][2] - pr.X[0][2];
+    const double al = wx * e1x + wy * e1y + wz * e1z, be = wx * e2x + wy * e2y + wz * e2z, ga = wx * e3x + wy * e3y + wz * e3z;
+    const double lim2 = (thr + 1.0) * (thr + 1.0);
+    for (int i = 0; i < 4; i++) {
+        if (i >= nroots) break;
+        double x = xr[i];
+        const double Dn = D1 * x + D0;
+        if (!(fabs(Dn) > 2e-3 * (fabs(D1 * x) + fabs(D0)))) return true;   // (the full solve switches formula at 1e-3)
+        double y = -((N2 * x + N1) * x + N0) / Dn;
+        const double f1 = (1 - a) * y * y - a * x * x - p * y + a * r * x * y + 1;
+        const double f2 = (1 - b) * x * x - b * y * y - q * x + b * r * x * y + 1;
+        const double j11 = -2 * a * x + a * r * y, j12 = 2 * (1 - a) * y - p + a * r * x;
+        const double j21 = 2 * (1 - b) * x - q + b * r * y, j22 = -2 * b * y + b * r * x;
+        const double det = j11 * j22 - j12 * j21;
+        const double jn = j11 * j11 + j12 * j12 + j21 * j21 + j22 * j22;
+        if (!(fabs(det) > 1e-4 * jn)) return true;
+        const double idet = 1.0 / det;
+        const double dx = (f1 * j22 - f2 * j12) * idet, dy = (j11 * f2 - j21 * f1) * idet;
+        x -= dx;
+        y -= dy;
+        if (!(fabs(dx) + fabs(dy) <= 1e-6 * (fabs(x) + fabs(y)))) return true;
+        if (x < -1e-6 || y < -1e-6) continue;
+        if (x < 1e-6 || y < 1e-6) return true;
+        const double v = x * x + y * y - x * y * r;
+        if (!(v > 1e-12)) return true;
+        const double Z = d01 * rsqrt_or(v);
+        const double L0 = x * Z, L1 = y * Z;
+        const double M0x = L0 * bear[0][0], M0y = L0 * bear[0][1], M0z = L0 * bear[0][2];
+        const double ux = L1 * bear[1][0] - M0x, uy = L1 * bear[1][1] - M0y, uz = L1 * bear[1][2] - M0z;
+        const double vx = Z * bear[2][0] - M0x, vy = Z * bear[2][1] - M0y, vz = Z * bear[2][2] - M0z;
+        const double cxn = uy * vz - uz * vy, cyn = uz * vx - ux * vz, czn = ux * vy - uy * vx;
+        const double c1x = ux * inv_d, c1y = uy * inv_d, c1z = uz * inv_d;
+        const double c3x = cxn * inv_n, c3y = cyn * inv_n, c3z = czn * inv_n;
+        const double c2x = c3y * c1z - c3z * c1y, c2y = c3z * c1x - c3x * c1z, c2z = c3x * c1y - c3y * c1x;
+        const double X3 = M0x + al * c1x + be * c2x + ga * c3x;
+        const double Y3 = M0y + al * c1y + be * c2y + ga * c3y;
+        const double Z3 = M0z + al * c1z + be * c2z + ga * c3z;
+        const double iz = 1.0 / Z3;
+        const double du = cx + f * X3 * iz - pr.mu[3], dv = cy + f * Y3 * iz - pr.mv[3];
+        const double e2 = du * du + dv * dv;
+        if (!(e2 > lim2)) return true;
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------------------------------
 // fp32 version of the conservative filter.  Same decision contract as p3p_quick_needs_full
 // ("false" only if the candidate is certainly rejected), but every quantity whose rounding
@@ -650,10 +788,8 @@ DSAC_HDN bool minimal_set_needs_full_f32(const float obj[12], const float img[8]
 }
 
 // Quick conservative pre-test of a minimal set (see p3p_quick_needs_full).
-DSAC_HDN bool minimal_set_needs_full_pr(const P3PProblem& pr, double f, double cx, double cy, int thr) {
-    P3PFront fr;
-    p3p_front(pr, f, cx, cy, fr);
-    return p3p_quick_needs_full(pr, fr, f, cx, cy, (double)thr);
+DSAC_HD bool minimal_set_needs_full_pr(const P3PProblem& pr, double f, double cx, double cy, int thr) {
+    return p3p_quick_inline(pr, f, cx, cy, 1.0 / f, (double)thr);
 }
 DSAC_HDN bool minimal_set_needs_full(const float obj[12], const float img[8], double f, double cx, double cy, int thr) {
     P3PProblem pr;
