@@ -318,27 +318,44 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
         // ---------------- phase D: full fp64 P3P + reprojection check (cnn_softam.h:1041-1059) on the
         //                  queue, then the first `quota` accepted candidates of the stream, in order
         int par = 0;
-        for (int base = 0; base < q_n && acc < quota; base += K1_THREADS, par ^= 1) {
-            const int qi = base + tid;
+        constexpr int GROUP = 4;   // lanes per flagged candidate: lane `sub` handles quartic root `sub`
+        for (int base = 0; base < q_n && acc < quota; base += K1_THREADS / GROUP, par ^= 1) {
+            const int qi = base + tid / GROUP, sub = tid % GROUP;
             bool ok = false, fragile = false;
             double rvec[3], tvec[3];
             int cells[4] = {0, 0, 0, 0};
             long long cand = 0;
+            double e2 = 1.7976931348623157e308, R[9], t[3];
+            float obj[12], img[8];
+            int nsol = 0;
             if (qi < q_n) {
                 int ci = sm.q_idx[qi];
                 cand_parse_fast(sm.vals, sm.cand_start[ci], w_avail, cells);
                 cand = cand_base + ci;
                 P3PProblem pr;
                 load_problem(cells, pr);
-                float obj[12], img[8];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     obj[j * 3] = (float)pr.X[j][0]; obj[j * 3 + 1] = (float)pr.X[j][1]; obj[j * 3 + 2] = (float)pr.X[j][2];
                     img[j * 2] = (float)__ldg(pix + cells[j] * 2);
                     img[j * 2 + 1] = (float)__ldg(pix + cells[j] * 2 + 1);
                 }
-                ok = minimal_set_hypothesis_pr(pr, obj, img, p.f, p.cx, p.cy, p.thr, rvec, tvec, &fragile);
+                P3PFront fr;
+                p3p_front(pr, p.f, p.cx, p.cy, fr);
+                nsol = p3p_full(pr, fr, p.f, p.cx, p.cy, R, t, &e2, sub, sub + 1);
+                if (nsol == 0) e2 = 1.7976931348623157e308;
             }
+            // minimum over the group; ties go to the lower root index, as the sequential loop would
+            double be = e2;
+            int bl = sub;
+#pragma unroll
+            for (int off = 1; off < GROUP; off <<= 1) {
+                double oe = __shfl_xor_sync(0xffffffffu, be, off);
+                int ol = __shfl_xor_sync(0xffffffffu, bl, off);
+                if (oe < be || (oe == be && ol < bl)) { be = oe; bl = ol; }
+            }
+            if (nsol > 0 && bl == sub)
+                ok = minimal_set_accept(obj, img, p.f, p.cx, p.cy, p.thr, R, t, e2, rvec, tvec, &fragile);
             if (fragile) atomicAdd(p.n_fragile, 1ull);
             int tot;
             int rank = acc + block_excl_scan_256(ok ? 1 : 0, &tot, sm.warp[par]);
@@ -347,12 +364,12 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
                 double* hp = p.hyp_pose + hi * 6;
                 hp[0] = rvec[0]; hp[1] = rvec[1]; hp[2] = rvec[2];
                 hp[3] = tvec[0]; hp[4] = tvec[1]; hp[5] = tvec[2];
-                double R[9];
-                rodrigues_v2m(rvec, R);  // getDiffMap -> cv::projectPoints rebuilds R from rvec
+                double Rm[9];
+                rodrigues_v2m(rvec, Rm);  // getDiffMap -> cv::projectPoints rebuilds R from rvec
                 float4* P = reinterpret_cast<float4*>(p.hyp_P + hi * 12);
-                P[0] = make_float4((float)(p.f * R[0]), (float)(p.f * R[1]), (float)(p.f * R[2]), (float)(p.f * tvec[0]));
-                P[1] = make_float4((float)(p.f * R[3]), (float)(p.f * R[4]), (float)(p.f * R[5]), (float)(p.f * tvec[1]));
-                P[2] = make_float4((float)R[6], (float)R[7], (float)R[8], (float)tvec[2]);
+                P[0] = make_float4((float)(p.f * Rm[0]), (float)(p.f * Rm[1]), (float)(p.f * Rm[2]), (float)(p.f * tvec[0]));
+                P[1] = make_float4((float)(p.f * Rm[3]), (float)(p.f * Rm[4]), (float)(p.f * Rm[5]), (float)(p.f * tvec[1]));
+                P[2] = make_float4((float)Rm[6], (float)Rm[7], (float)Rm[8], (float)tvec[2]);
                 *reinterpret_cast<int4*>(p.img_idx + hi * 4) = make_int4(cells[0], cells[1], cells[2], cells[3]);
                 p.cand_idx[hi] = (int32_t)cand;
                 if (rank == quota - 1) p.stream_ncand[(size_t)frame * p.T + s] = cand + 1;

@@ -320,8 +320,10 @@ DSAC_HD int p3p_y_candidates(const P3PFront& fr, double x0, double* ya, double* 
 // All P3P solutions from points 0..2 (given the front end), the one with the smallest squared
 // reprojection error of point 3 is returned (cv::solvePnP CV_P3P semantics).  Returns the
 // number of solutions; *best_err2 is that smallest squared error (pixels^2).
+// Only quartic roots with index in [root_lo, root_hi) are processed (the sampler's full-solve phase spreads
+// the roots of one candidate over a group of lanes and takes the minimum across them).
 DSAC_HDN int p3p_full(const P3PProblem& pr, const P3PFront& fr, double f, double cx, double cy, double Rbest[9],
-                      double tbest[3], double* best_err2) {
+                      double tbest[3], double* best_err2, int root_lo = 0, int root_hi = 4) {
     if (fr.nroots == 0) return 0;
     const double a = fr.a, b = fr.b, p = fr.p, q = fr.q, r = fr.r;
     double Ew[9], Cw[3];
@@ -331,7 +333,7 @@ DSAC_HDN int p3p_full(const P3PProblem& pr, const P3PFront& fr, double f, double
     double sx[4], sy[4];
     int ns = 0, nsol = 0;
     double best = 0;
-    for (int i = 0; i < fr.nroots; i++) {
+    for (int i = root_lo; i < fr.nroots && i < root_hi; i++) {
         double x0 = fr.xr[i];
         if (!(x0 == x0)) continue;
         double y0a, y0b;
@@ -477,13 +479,12 @@ DSAC_HD double p3p_pixel(float pix, double c, double f) {
 // Returns true if accepted; rvec/tvec are the cv pose.  *fragile is set when a decision
 // was within 1e-6 px of the threshold.  pr: the P3P problem (see make_problem); obj/img: the
 // float correspondences the reprojection check uses.
-DSAC_HDN bool minimal_set_hypothesis_pr(const P3PProblem& pr, const float obj[12], const float img[8], double f, double cx,
-                                        double cy, int thr, double rvec[3], double tvec[3], bool* fragile) {
-    double R[9], t[3], e2;
+// Second half of the sampling loop's test, given the P3P winner (R, t, e2 = its squared 4th-point error):
+// Rodrigues vector, then all 4 reprojection errors exactly as the reference measures them.
+DSAC_HDN bool minimal_set_accept(const float obj[12], const float img[8], double f, double cx, double cy, int thr,
+                                 const double R[9], const double t[3], double e2, double rvec[3], double tvec[3],
+                                 bool* fragile) {
     *fragile = false;
-    P3PFront fr;
-    p3p_front(pr, f, cx, cy, fr);
-    if (p3p_full(pr, fr, f, cx, cy, R, t, &e2) == 0) return false;
     // cheap exact-safe pre-check: the 4th point's error as P3P measured it differs from the
     // reference's float-rounded check by < 1e-4 px
     if (!(e2 < ((double)thr + 1e-3) * ((double)thr + 1e-3))) return false;
@@ -501,6 +502,16 @@ DSAC_HDN bool minimal_set_hypothesis_pr(const P3PProblem& pr, const float obj[12
         if (!(nrm < thr)) ok = false;
     }
     return ok;
+}
+
+DSAC_HDN bool minimal_set_hypothesis_pr(const P3PProblem& pr, const float obj[12], const float img[8], double f, double cx,
+                                        double cy, int thr, double rvec[3], double tvec[3], bool* fragile) {
+    double R[9], t[3], e2;
+    *fragile = false;
+    P3PFront fr;
+    p3p_front(pr, f, cx, cy, fr);
+    if (p3p_full(pr, fr, f, cx, cy, R, t, &e2) == 0) return false;
+    return minimal_set_accept(obj, img, f, cx, cy, thr, R, t, e2, rvec, tvec, fragile);
 }
 
 DSAC_HD void make_problem(const float obj[12], const float img[8], double f, double cx, double cy, P3PProblem& pr) {
