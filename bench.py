@@ -321,6 +321,32 @@ def main():
                   "hyp_per_s": H / (us * 1e-6)}
         eng1.close()
 
+    # ---- config 3: 256 hyp, 8 refinement iterations + soft-argmax backward (one training round per frame)
+    train = None
+    if rank == 0:
+        nb3 = 64
+        eng3 = E.Engine(max_frames=nb3, device=local_rank)
+        eng3.forward(coords[:nb3], pix[:nb3], gt_jp[:nb3])
+        eng3.backward(coords[:nb3], pix[:nb3], gt_jp[:nb3], full=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps3 = 3
+        for _ in range(reps3):
+            eng3.forward(coords[:nb3], pix[:nb3], gt_jp[:nb3])
+            eng3.backward(coords[:nb3], pix[:nb3], gt_jp[:nb3], full=False)
+        torch.cuda.synchronize()
+        ms_round = (time.perf_counter() - t0) * 1e3 / (reps3 * nb3)
+        train = {"workload": "config 3: forward + backward (train_ransac_softam round), %d frames per call, host buffers" % nb3,
+                 "gpu_ms_per_round": ms_round, "rounds_per_s": 1e3 / ms_round}
+        if world == 1:
+            from oracle import oracle as O
+            cfg3 = O.default_config(seed=1305 + frame0)
+            t0 = time.perf_counter()
+            ofw = O.forward(cfg3, coords[0], pix[0], gt_jp[0, :9], gt_jp[0, 9:])
+            O.backward(cfg3, coords[0], pix[0], gt_jp[0, :9], gt_jp[0, 9:], ofw)
+            train["cpu_ms_per_round_1thread"] = (time.perf_counter() - t0) * 1e3
+        eng3.close()
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
     cpu = None
     if rank == 0 and world == 1:
@@ -352,6 +378,7 @@ def main():
             "kernels_ms": stage_ms,
             "cpu_baseline": cpu,
             "single_frame": single,
+            "train_round": train,
             "quality": quality,
             "clocks": clk,
         }
