@@ -37,7 +37,7 @@ int main(int argc, const char* argv[]) {
     std::vector<FrameResult> all(nFrames);
     std::vector<int> rcs(nGpus, 0);
     std::vector<std::string> errs(nGpus);
-    auto t0 = std::chrono::high_resolution_clock::now();
+    std::vector<double> busy(nGpus, 0.0);   // seconds inside processImages per GPU
     // frames are independent: contiguous shards, one engine + host thread per GPU, no collective
     std::vector<std::thread> workers;
     for (int g = 0; g < nGpus; g++)
@@ -56,7 +56,9 @@ int main(int argc, const char* argv[]) {
                 dsac_synth_frames(20170721u, gp->eP.seed, gp->eP.streams, f0, n, gp->eP.inlierRatio, gp->eP.noise,
                                   gp->eP.trajectory, cfg.focal, cfg.cx, cfg.cy, coords.data(), pix.data(), nullptr, gtJp.data());
                 std::vector<FrameResult> res;
+                auto t0 = std::chrono::high_resolution_clock::now();
                 int rc = processImages(eng, n, f0, coords.data(), pix.data(), gtJp.data(), res);
+                busy[g] += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
                 if (rc != DSAC_OK) { rcs[g] = rc; errs[g] = dsac_last_error(eng); break; }
                 for (int i = 0; i < n; i++) all[f0 + i] = std::move(res[i]);
             }
@@ -65,7 +67,8 @@ int main(int argc, const char* argv[]) {
     for (auto& w : workers) w.join();
     for (int g = 0; g < nGpus; g++)
         if (rcs[g] != 0) { std::cerr << "engine on GPU " << g << " failed: " << errs[g] << std::endl; return 1; }
-    double secs = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    double secs = 0;
+    for (double b : busy) secs = std::max(secs, b);
 
     const std::string tag = modelFileRGB + "_rdraw" + std::to_string((int)gp->pP.randomDraw) + "_softam.txt";
     std::ofstream testFile("ransac_test_loss_" + tag), testErrFile("ransac_test_errors_" + tag);
@@ -107,7 +110,7 @@ int main(int argc, const char* argv[]) {
     std::cout << "Avg. test loss: " << lossMean << ", accuracy: " << avgCorrect * 100 << "%" << std::endl;
     std::cout << "Median Rot. Error: " << medianRotErr << "deg, Median T. Error: " << medianTErr / 10 << "cm." << std::endl;
     std::cout << nFrames << " frames x " << objHyps << " hypotheses on " << nGpus << " GPU(s) in " << secs << " s: "
-              << nFrames / secs << " frames/s, " << (double)nFrames * objHyps / secs << " hypotheses/s (incl. synthetic data generation)" << std::endl;
+              << nFrames / secs << " frames/s, " << (double)nFrames * objHyps / secs << " hypotheses/s (time inside processImages: H2D + kernels + D2H + unpacking; max over GPUs)" << std::endl;
     testFile << avgCorrect << " " << lossMean << " " << lossSd << " " << entMean << " " << entSd << " " << medianRotErr << " "
              << medianTErr << std::endl;
     return 0;

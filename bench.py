@@ -304,22 +304,27 @@ def main():
     # ---- config 2: single frame latency (1 frame, 256 hyp, forward scoring + soft-argmax)
     single = None
     if rank == 0:
-        eng1 = E.Engine(max_frames=1, device=local_rank)
-        eng1.set_stages(E.STAGE_SAMPLE | E.STAGE_SCORE)
-        for _ in range(20):
-            eng1.forward_device(1, d_coords.data_ptr(), d_pix.data_ptr(), 0, d_gt.data_ptr(), frame0, stream)
-        torch.cuda.synchronize()
-        reps = 200
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            eng1.forward_device(1, d_coords.data_ptr(), d_pix.data_ptr(), 0, d_gt.data_ptr(), frame0, stream)
-        e1.record()
-        e1.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / reps
-        single = {"workload": "config 2: 1 frame x 256 hyp x 1600 pts, sample+score+soft-argmax", "latency_us": us,
-                  "hyp_per_s": H / (us * 1e-6)}
-        eng1.close()
+        single = {"workload": "config 2: 1 frame x 256 hyp x 1600 pts, sample+score+soft-argmax (CUDA events, 200 reps)"}
+        # n_streams is part of the sampler contract (= OpenMP threads of the reference loop): 1 reproduces
+        # OMP_NUM_THREADS=1, 8 an 8-thread run; more streams = more CTAs sampling the one frame in parallel
+        for T in (1, 8):
+            d1 = E.synth_frames(1, frame0=frame0, n_streams=T)
+            c1 = torch.from_numpy(d1[0]).cuda(); p1 = torch.from_numpy(d1[1]).cuda(); g1 = torch.from_numpy(d1[3]).cuda()
+            eng1 = E.Engine(max_frames=1, device=local_rank, n_streams=T)
+            eng1.set_stages(E.STAGE_SAMPLE | E.STAGE_SCORE)
+            for _ in range(20):
+                eng1.forward_device(1, c1.data_ptr(), p1.data_ptr(), 0, g1.data_ptr(), frame0, stream)
+            torch.cuda.synchronize()
+            reps = 200
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                eng1.forward_device(1, c1.data_ptr(), p1.data_ptr(), 0, g1.data_ptr(), frame0, stream)
+            e1.record()
+            e1.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            single["streams_%d" % T] = {"latency_us": us, "hyp_per_s": H / (us * 1e-6)}
+            eng1.close()
 
     # ---- config 3: 256 hyp, 8 refinement iterations + soft-argmax backward (one training round per frame)
     train = None

@@ -68,6 +68,7 @@ struct dsac_engine {
     unsigned int* d_frame_counter = nullptr;
     std::vector<long long> h_stream_ncand;
     BackwardScratch bw;
+    cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // chunked H2D / compute / D2H pipeline of dsac_forward
 };
 
 static int fail(dsac_engine* e, int code, const char* fmt, ...) {
@@ -127,6 +128,8 @@ int dsac_engine_config(const dsac_engine* e, dsac_config* out) {
 void dsac_engine_destroy(dsac_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    for (cudaStream_t st : e->pipe)
+        if (st) cudaStreamDestroy(st);
     if (e->d_phase) {
         unsigned long long h[16];
         if (cudaMemcpy(h, e->d_phase, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -235,6 +238,7 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
     }
     CUC(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
     e->h_stream_ncand.resize(n * cfg->n_streams);
+    for (int i = 0; i < 4; i++) CUC(cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking));
 #undef CUC
     *out = e;
     return DSAC_OK;
@@ -268,31 +272,24 @@ static int pick_tile(const dsac_engine* e, int n_frames) {
     return t;
 }
 
-int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* d_coords, const int32_t* d_pix,
-                        int32_t pix_shared, const double* d_gt_jp, void* stream_v) {
-    if (!e) return DSAC_ERR_ARG;
-    if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
-    if (!d_coords || !d_pix) return fail(e, DSAC_ERR_ARG, "null input");
+// Launches the forward stages for `n` frames whose per-frame engine buffers start at frame offset `off`
+// (inputs are passed already offset).  Used whole (off = 0) and per chunk by the pipelined host path.
+static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0, const int16_t* d_coords, const int32_t* d_pix,
+                         int32_t pix_shared, const double* d_gt_jp, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     const dsac_config& c = e->cfg;
-    CU(cudaSetDevice(c.device));
-    e->cur_coords = d_coords;
-    e->cur_pix = d_pix;
-    e->cur_pix_shared = pix_shared;
-    e->cur_gt = d_gt_jp;
-    e->cur_n = n;
-    e->cur_frame0 = frame0;
+    const size_t o = (size_t)off, Hh = (size_t)c.n_hyps, Nn = DSAC_N;
 
     if (e->stages & DSAC_STAGE_SAMPLE) {
-        CU(cudaMemsetAsync(e->d_status, 0, (size_t)n * sizeof(uint32_t), stream));
+        CU(cudaMemsetAsync(e->d_status + o, 0, (size_t)n * sizeof(uint32_t), stream));
         SampleParams sp;
         sp.coords = d_coords; sp.pix = d_pix; sp.pix_stride = pix_shared ? 0 : DSAC_N * 2;
         sp.f = c.focal; sp.cx = c.cx; sp.cy = c.cy;
         sp.H = c.n_hyps; sp.T = c.n_streams; sp.thr = c.thr2d;
         sp.seed = c.seed; sp.skip = c.stream_skip; sp.max_candidates = c.max_candidates;
         sp.frame0 = frame0;
-        sp.hyp_pose = e->d_hyp_pose; sp.hyp_P = e->d_hyp_P; sp.img_idx = e->d_img_idx; sp.cand_idx = e->d_cand_idx;
-        sp.stream_ncand = e->d_stream_ncand; sp.status = e->d_status; sp.n_fragile = e->d_fragile;
+        sp.hyp_pose = e->d_hyp_pose + o * Hh * 6; sp.hyp_P = e->d_hyp_P + o * Hh * 12; sp.img_idx = e->d_img_idx + o * Hh * 4; sp.cand_idx = e->d_cand_idx + o * Hh;
+        sp.stream_ncand = e->d_stream_ncand + o * c.n_streams; sp.status = e->d_status + o; sp.n_fragile = e->d_fragile;
         sp.phase_cycles = e->d_phase;
         k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);
         e->launches++;
@@ -301,9 +298,9 @@ int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
     if (e->stages & DSAC_STAGE_SCORE) {
         ScoreParams kp;
         kp.coords = d_coords; kp.pix = d_pix; kp.pix_stride = pix_shared ? 0 : DSAC_N * 2;
-        kp.hyp_P = e->d_hyp_P; kp.hyp_pose = e->d_hyp_pose;
-        kp.diffmaps = e->d_diffmaps; kp.scores = e->d_scores; kp.sf = e->d_sf; kp.entropy = e->d_entropy;
-        kp.avg_pose = e->d_avg; kp.frame_counter = e->d_frame_counter;
+        kp.hyp_P = e->d_hyp_P + o * Hh * 12; kp.hyp_pose = e->d_hyp_pose + o * Hh * 6;
+        kp.diffmaps = e->d_diffmaps ? e->d_diffmaps + o * Hh * Nn : nullptr; kp.scores = e->d_scores + o * Hh; kp.sf = e->d_sf + o * Hh; kp.entropy = e->d_entropy + o;
+        kp.avg_pose = e->d_avg + o * 6; kp.frame_counter = e->d_frame_counter + o;
         kp.H = c.n_hyps;
         kp.tile = pick_tile(e, n);
         kp.tiles_per_frame = (c.n_hyps + kp.tile - 1) / kp.tile;
@@ -320,7 +317,7 @@ int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
         if (e->hook) {
             // score seam (lua_calls.h:284-300): external scorer on the materialised diffmaps,
             // then only the softmax / soft-argmax tail
-            int rc = e->hook(e->d_diffmaps, n, c.n_hyps, e->d_scores, stream_v, e->hook_user);
+            int rc = e->hook(kp.diffmaps, n, c.n_hyps, kp.scores, stream_v, e->hook_user);
             if (rc != 0) return fail(e, DSAC_ERR_ARG, "score hook returned %d", rc);
             kp.external_scores = 1;
             kp.tiles_per_frame = 1;
@@ -337,13 +334,13 @@ int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
         rp.f = c.focal; rp.cx = c.cx; rp.cy = c.cy;
         rp.thr = c.thr2d; rp.inlier_count = c.inlier_count; rp.ref_steps = c.ref_steps;
         rp.n_jobs = n;
-        rp.job_init = e->d_avg;
-        rp.out_pose = e->d_ref;
-        rp.inlier_map = e->d_inlier_map; rp.steps_done = e->d_steps_done; rp.n_perm_steps = e->d_n_perm;
-        rp.status = e->d_status;
+        rp.job_init = e->d_avg + o * 6;
+        rp.out_pose = e->d_ref + o * 6;
+        rp.inlier_map = e->d_inlier_map + o * Nn; rp.steps_done = e->d_steps_done + o; rp.n_perm_steps = e->d_n_perm + o;
+        rp.status = e->d_status + o;
         if ((e->stages & DSAC_STAGE_EVAL) && d_gt_jp) {
             rp.gt_jp = d_gt_jp;
-            rp.loss = e->d_loss; rp.rot_err = e->d_rot_err; rp.t_err = e->d_t_err; rp.correct = e->d_correct;
+            rp.loss = e->d_loss + o; rp.rot_err = e->d_rot_err + o; rp.t_err = e->d_t_err + o; rp.correct = e->d_correct + o;
         }
         k_refine<<<n, K4_THREADS, 0, stream>>>(rp);
         e->launches++;
@@ -352,45 +349,76 @@ int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
     return DSAC_OK;
 }
 
+int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* d_coords, const int32_t* d_pix,
+                        int32_t pix_shared, const double* d_gt_jp, void* stream_v) {
+    if (!e) return DSAC_ERR_ARG;
+    if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
+    if (!d_coords || !d_pix) return fail(e, DSAC_ERR_ARG, "null input");
+    CU(cudaSetDevice(e->cfg.device));
+    e->cur_coords = d_coords;
+    e->cur_pix = d_pix;
+    e->cur_pix_shared = pix_shared;
+    e->cur_gt = d_gt_jp;
+    e->cur_n = n;
+    e->cur_frame0 = frame0;
+    return forward_range(e, 0, n, frame0, d_coords, d_pix, pix_shared, d_gt_jp, stream_v);
+}
+
+// Queues the device->host copies of frames [off, off+n) into the caller's buffers (no synchronisation).
+static int fetch_range(dsac_engine* e, int32_t off, int32_t n, dsac_forward_out* o, cudaStream_t stream) {
+    const size_t H = e->cfg.n_hyps, N = DSAC_N, T = e->cfg.n_streams, nn = (size_t)n, f = (size_t)off;
+#define D2H(dst, src, per)                                                                                          \
+    do {                                                                                                            \
+        if ((dst) && (src))                                                                                         \
+            CU(cudaMemcpyAsync((dst) + f * (per), (src) + f * (per), nn * (per) * sizeof(*(dst)), cudaMemcpyDeviceToHost, stream)); \
+    } while (0)
+    D2H(o->hyp_pose, e->d_hyp_pose, H * 6);
+    D2H(o->img_idx, e->d_img_idx, H * 4);
+    D2H(o->cand_idx, e->d_cand_idx, H);
+    D2H(o->scores, e->d_scores, H);
+    D2H(o->sf, e->d_sf, H);
+    if (o->diffmaps) {
+        if (!e->d_diffmaps) return fail(e, DSAC_ERR_ARG, "diffmaps requested but the engine was created with write_diffmaps=0");
+        D2H(o->diffmaps, e->d_diffmaps, H * N);
+    }
+    D2H(o->entropy, e->d_entropy, 1);
+    D2H(o->avg_pose, e->d_avg, 6);
+    D2H(o->ref_pose, e->d_ref, 6);
+    D2H(o->inlier_map, e->d_inlier_map, N);
+    D2H(o->ref_steps_done, e->d_steps_done, 1);
+    D2H(o->n_perm_steps, e->d_n_perm, 1);
+    D2H(o->loss, e->d_loss, 1);
+    D2H(o->rot_err, e->d_rot_err, 1);
+    D2H(o->t_err, e->d_t_err, 1);
+    D2H(o->correct, e->d_correct, 1);
+    D2H(o->status, e->d_status, 1);
+    if (o->n_candidates) {
+        long long* hdst = e->h_stream_ncand.data();
+        D2H(hdst, e->d_stream_ncand, T);
+    }
+#undef D2H
+    return DSAC_OK;
+}
+
+static void sum_candidates(dsac_engine* e, int32_t n, dsac_forward_out* o) {
+    const size_t T = e->cfg.n_streams;
+    if (!o->n_candidates) return;
+    for (size_t f = 0; f < (size_t)n; f++) {
+        long long s = 0;
+        for (size_t t = 0; t < T; t++) s += e->h_stream_ncand[f * T + t];
+        o->n_candidates[f] = s;
+    }
+}
+
 int dsac_fetch(dsac_engine* e, int32_t n, dsac_forward_out* o, void* stream_v) {
     if (!e || !o) return DSAC_ERR_ARG;
     if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
     cudaStream_t stream = (cudaStream_t)stream_v;
-    const size_t H = e->cfg.n_hyps, N = DSAC_N, T = e->cfg.n_streams, nn = (size_t)n;
     CU(cudaSetDevice(e->cfg.device));
-#define D2H(dst, src, bytes)                                                                    \
-    do {                                                                                        \
-        if ((dst) && (src)) CU(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, stream)); \
-    } while (0)
-    D2H(o->hyp_pose, e->d_hyp_pose, nn * H * 6 * sizeof(double));
-    D2H(o->img_idx, e->d_img_idx, nn * H * 4 * sizeof(int32_t));
-    D2H(o->cand_idx, e->d_cand_idx, nn * H * sizeof(int32_t));
-    D2H(o->scores, e->d_scores, nn * H * sizeof(double));
-    D2H(o->sf, e->d_sf, nn * H * sizeof(double));
-    if (o->diffmaps) {
-        if (!e->d_diffmaps) return fail(e, DSAC_ERR_ARG, "diffmaps requested but the engine was created with write_diffmaps=0");
-        D2H(o->diffmaps, e->d_diffmaps, nn * H * N * sizeof(float));
-    }
-    D2H(o->entropy, e->d_entropy, nn * sizeof(double));
-    D2H(o->avg_pose, e->d_avg, nn * 6 * sizeof(double));
-    D2H(o->ref_pose, e->d_ref, nn * 6 * sizeof(double));
-    D2H(o->inlier_map, e->d_inlier_map, nn * N * sizeof(int32_t));
-    D2H(o->ref_steps_done, e->d_steps_done, nn * sizeof(int32_t));
-    D2H(o->n_perm_steps, e->d_n_perm, nn * sizeof(int32_t));
-    D2H(o->loss, e->d_loss, nn * sizeof(double));
-    D2H(o->rot_err, e->d_rot_err, nn * sizeof(double));
-    D2H(o->t_err, e->d_t_err, nn * sizeof(double));
-    D2H(o->correct, e->d_correct, nn * sizeof(int32_t));
-    D2H(o->status, e->d_status, nn * sizeof(uint32_t));
-    if (o->n_candidates) D2H(e->h_stream_ncand.data(), e->d_stream_ncand, nn * T * sizeof(long long));
-#undef D2H
+    int rc = fetch_range(e, 0, n, o, stream);
+    if (rc != DSAC_OK) return rc;
     CU(cudaStreamSynchronize(stream));
-    if (o->n_candidates)
-        for (size_t f = 0; f < nn; f++) {
-            long long s = 0;
-            for (size_t t = 0; t < T; t++) s += e->h_stream_ncand[f * T + t];
-            o->n_candidates[f] = s;
-        }
+    sum_candidates(e, n, o);
     return DSAC_OK;
 }
 
@@ -412,15 +440,41 @@ int dsac_forward(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coord
     if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
     if (!coords || !pix) return fail(e, DSAC_ERR_ARG, "null input");
     CU(cudaSetDevice(e->cfg.device));
-    cudaStream_t stream = 0;
-    const size_t N = DSAC_N, nn = (size_t)n;
-    CU(cudaMemcpyAsync(e->d_coords, coords, nn * N * 3 * sizeof(int16_t), cudaMemcpyHostToDevice, stream));
-    CU(cudaMemcpyAsync(e->d_pix, pix, (pix_shared ? 1 : nn) * N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-    if (gt_jp) CU(cudaMemcpyAsync(e->d_gt, gt_jp, nn * 12 * sizeof(double), cudaMemcpyHostToDevice, stream));
-    int rc = dsac_forward_device(e, n, frame0, e->d_coords, e->d_pix, pix_shared, gt_jp ? e->d_gt : nullptr, stream);
-    if (rc != DSAC_OK) return rc;
-    if (out) return dsac_fetch(e, n, out, stream);
-    CU(cudaStreamSynchronize(stream));
+    const size_t N = DSAC_N;
+    e->cur_coords = e->d_coords;
+    e->cur_pix = e->d_pix;
+    e->cur_pix_shared = pix_shared;
+    e->cur_gt = gt_jp ? e->d_gt : nullptr;
+    e->cur_n = n;
+    e->cur_frame0 = frame0;
+    // Frames are independent, so the batch is cut into up to 4 chunks, each on its own stream:
+    // H2D(chunk) -> K1 -> K2 -> K4 -> D2H(chunk).  Copies of later chunks overlap the kernels of earlier
+    // ones and the tail of one chunk's kernels is filled by the next chunk's CTAs.
+    int chunks = 1;   // measured on B200 (tools/e2e_probe.py): 1 chunk 6.03 ms, 2: 6.21, 4: 6.87 -- the sampler kernel wants the whole batch
+    if (const char* ev = getenv("DSAC_PIPE_CHUNKS")) chunks = std::max(1, std::min(4, atoi(ev)));
+    if (pix_shared) CU(cudaMemcpyAsync(e->d_pix, pix, N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, e->pipe[0]));
+    if (pix_shared && chunks > 1) {   // every chunk reads the shared grid: make it visible to all streams first
+        CU(cudaStreamSynchronize(e->pipe[0]));
+    }
+    for (int c = 0; c < chunks; c++) {
+        const int lo = (int)((long long)n * c / chunks), hi = (int)((long long)n * (c + 1) / chunks), m = hi - lo;
+        if (m <= 0) continue;
+        cudaStream_t st = e->pipe[c];
+        const size_t f = (size_t)lo;
+        CU(cudaMemcpyAsync(e->d_coords + f * N * 3, coords + f * N * 3, (size_t)m * N * 3 * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        if (!pix_shared)
+            CU(cudaMemcpyAsync(e->d_pix + f * N * 2, pix + f * N * 2, (size_t)m * N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (gt_jp) CU(cudaMemcpyAsync(e->d_gt + f * 12, gt_jp + f * 12, (size_t)m * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+        int rc = forward_range(e, lo, m, frame0 + lo, e->d_coords + f * N * 3, pix_shared ? e->d_pix : e->d_pix + f * N * 2,
+                               pix_shared, gt_jp ? e->d_gt + f * 12 : nullptr, st);
+        if (rc != DSAC_OK) return rc;
+        if (out) {
+            rc = fetch_range(e, lo, m, out, st);
+            if (rc != DSAC_OK) return rc;
+        }
+    }
+    for (int c = 0; c < chunks; c++) CU(cudaStreamSynchronize(e->pipe[c]));
+    if (out) sum_candidates(e, n, out);
     return DSAC_OK;
 }
 
