@@ -17,9 +17,10 @@
 namespace dsac {
 
 // ------------------------------------------------------------------ block helpers
-// Exclusive prefix sum over a 256-thread block (+ block total).  One barrier: consecutive calls must
+// Exclusive prefix sum over a block of NWARPS warps (+ block total).  One barrier: consecutive calls must
 // use different s_warp buffers.
-__device__ __forceinline__ int block_excl_scan_256(int v, int* total, int* s_warp /* >= 8 ints */) {
+template <int NWARPS>
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int* s_warp /* >= NWARPS ints */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = v;
 #pragma unroll
@@ -31,7 +32,7 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* total, int* s_war
     __syncthreads();
     int base = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
+    for (int w = 0; w < NWARPS; w++) {
         int x = s_warp[w];
         if (w < warp) base += x;
         tot += x;
@@ -60,9 +61,13 @@ struct SampleParams {
     unsigned long long* phase_cycles;  // [8] or null: thread-0 cycles per phase (development aid)
 };
 
-constexpr int K1_THREADS = 256;
+#ifndef K1_THREADS_DEF
+#define K1_THREADS_DEF 256
+#endif
+constexpr int K1_THREADS = K1_THREADS_DEF;
+constexpr int K1_WARPS = K1_THREADS / 32;
 #ifndef K1_MIN_BLOCKS
-#define K1_MIN_BLOCKS 2
+#define K1_MIN_BLOCKS (512 / K1_THREADS_DEF)
 #endif
 constexpr int K1_SUPER_MAX = 16;                          // x256 candidates per super-round
 constexpr int K1_CANDS = K1_SUPER_MAX * K1_THREADS;       // candidates buffered per super-round
@@ -71,9 +76,10 @@ constexpr int K1_WAVE = MT_N - MT_M;                      // 227 new MT19937 wor
 
 // Per-cell record staged in shared memory: scene coordinate (mm) and the float-rounded
 // normalised pixel that cv::undistortPoints hands to P3P.
-struct __align__(16) CellRec {
-    short X, Y, Z, pad;
-    float xn, yn;
+struct __align__(4) CellRec {
+    short X, Y, Z;   // scene coordinate, mm
+    short u, v;      // sampling pixel
+    short pad;
 };
 
 struct K1Smem {
@@ -84,7 +90,7 @@ struct K1Smem {
     unsigned short q_idx[K1_CANDS];             // queue of candidates that need the full solve, ascending
     uint32_t flagbits[K1_CANDS / 32];
     uint32_t wordbase[K1_CANDS / 32];
-    int warp[2][8];
+    int warp[2][K1_WARPS];
     uint32_t newpos;
     int q_n, n_sr, any_reject, walk_fail;
 };
@@ -157,12 +163,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
     const int16_t* coords = p.coords + (size_t)frame * DSAC_N_CONST * 3;
     const int32_t* pix = p.pix + (size_t)frame * p.pix_stride;
     {
-        const double inv_f = 1. / p.f;
         for (int c = tid; c < DSAC_N_CONST; c += K1_THREADS) {
             CellRec r;
-            r.X = __ldg(coords + c * 3); r.Y = __ldg(coords + c * 3 + 1); r.Z = __ldg(coords + c * 3 + 2); r.pad = 0;
-            r.xn = (float)(((double)(float)__ldg(pix + c * 2) - p.cx) * inv_f);      // == p3p_pixel's rounding
-            r.yn = (float)(((double)(float)__ldg(pix + c * 2 + 1) - p.cy) * inv_f);
+            r.X = __ldg(coords + c * 3); r.Y = __ldg(coords + c * 3 + 1); r.Z = __ldg(coords + c * 3 + 2);
+            r.u = (short)__ldg(pix + c * 2); r.v = (short)__ldg(pix + c * 2 + 1); r.pad = 0;
             sm.cell[c] = r;
         }
     }
@@ -176,12 +180,15 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
     const long long cand_max = p.max_candidates > 0 ? (long long)p.max_candidates : (1ll << 40);
     int S = 4;                              // x256 candidates in the next super-round (adapted to the acceptance rate)
 
+    const double k1_inv_f = 1. / p.f;
     auto load_problem = [&](const int cells[4], P3PProblem& pr) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const CellRec r = sm.cell[cells[j]];
-            pr.mu[j] = r.xn * p.f + p.cx;   // float * double, as p3p_pixel
-            pr.mv[j] = r.yn * p.f + p.cy;
+            const float xn = (float)(((double)r.u - p.cx) * k1_inv_f);   // cv::undistortPoints rounds to float (p3p_pixel)
+            const float yn = (float)(((double)r.v - p.cy) * k1_inv_f);
+            pr.mu[j] = xn * p.f + p.cx;   // float * double
+            pr.mv[j] = yn * p.f + p.cy;
             pr.X[j][0] = (double)r.X; pr.X[j][1] = (double)r.Y; pr.X[j][2] = (double)r.Z;
         }
     };
@@ -196,11 +203,11 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
         const int w_need = min(K1_WORDS - 256, n_target * 8 + 768);   // a wave may overshoot by 226 words
         // (leftover words [pos, gen) were moved to vals[0..gen-pos) at the end of the previous super-round)
         while ((int)(gen - pos) < w_need) {
-            if (tid < K1_WAVE) {
-                uint32_t n = gen + MT_N + tid;  // linear index of the new element
+            for (int el = tid; el < K1_WAVE; el += K1_THREADS) {
+                uint32_t n = gen + MT_N + el;  // linear index of the new element
                 uint32_t x = mt_twist(sm.st[(n - MT_N) & 1023], sm.st[(n - MT_N + 1) & 1023], sm.st[(n - K1_WAVE) & 1023]);
                 sm.st[n & 1023] = x;
-                int off = (int)(gen + tid - pos);
+                int off = (int)(gen + el - pos);
                 if (off >= 0 && off < K1_WORDS) {
                     uint64_t prod = (uint64_t)mt_temper(x) * DSAC_GRID_CONST;
                     bool rej = (uint32_t)prod < ((0u - DSAC_GRID_CONST) % DSAC_GRID_CONST);  // Lemire: low < 2^32 mod 40
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
                 int extra = 0, start = 0, qn = 0;
                 for (;;) {
                     int tot;
-                    const int excl = block_excl_scan_256(extra, &tot, sm.warp[par]);
+                    const int excl = block_excl_scan<K1_WARPS>(extra, &tot, sm.warp[par]);
                     par ^= 1;
                     start = rp + 8 * tid + excl;
                     int cells[4];
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
                 __syncthreads();
                 int n_ok = n_chunk;
 #pragma unroll
-                for (int w = 0; w < 8; w++) n_ok = min(n_ok, sm.warp[par][w]);
+                for (int w = 0; w < K1_WARPS; w++) n_ok = min(n_ok, sm.warp[par][w]);
                 par ^= 1;
                 if (tid < n_ok) sm.cand_start[n_done + tid] = (unsigned short)start;
                 if (tid == n_ok - 1) sm.newpos = (uint32_t)qn;          // end of the last complete candidate
@@ -358,7 +365,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
                 ok = minimal_set_accept(obj, img, p.f, p.cx, p.cy, p.thr, R, t, e2, rvec, tvec, &fragile);
             if (fragile) atomicAdd(p.n_fragile, 1ull);
             int tot;
-            int rank = acc + block_excl_scan_256(ok ? 1 : 0, &tot, sm.warp[par]);
+            int rank = acc + block_excl_scan<K1_WARPS>(ok ? 1 : 0, &tot, sm.warp[par]);
             if (ok && rank < quota) {
                 size_t hi = (size_t)frame * p.H + h0 + rank;
                 double* hp = p.hyp_pose + hi * 6;
