@@ -49,6 +49,11 @@ struct dsac_engine {
     int32_t* d_img_idx = nullptr;
     int32_t* d_cand_idx = nullptr;
     long long* d_stream_ncand = nullptr;
+    unsigned long long* d_stream_endpos = nullptr;
+    // refine-all (DSAC variant) buffers, allocated on first use
+    int32_t* d_ra_frame = nullptr; double* d_ra_pose = nullptr; double* d_ra_loss = nullptr; double* d_ra_rot = nullptr;
+    double* d_ra_t = nullptr; int32_t* d_ra_correct = nullptr; int32_t* d_ra_steps = nullptr; int32_t* d_ra_imap = nullptr;
+    size_t ra_jobs = 0, ra_imap_jobs = 0;
     uint32_t* d_status = nullptr;
     unsigned long long* d_fragile = nullptr;
     unsigned long long* d_phase = nullptr;   // K1 per-phase cycle counters (DSAC_K1_TIMERS=1), else null
@@ -137,7 +142,8 @@ void dsac_engine_destroy(dsac_engine* e) {
         cudaFree(e->d_phase);
     }
     void* ptrs[] = {e->d_coords, e->d_pix, e->d_gt, e->d_perm, e->d_hyp_pose, e->d_hyp_P, e->d_img_idx, e->d_cand_idx,
-                    e->d_stream_ncand, e->d_status, e->d_fragile, e->d_diffmaps, e->d_scores, e->d_sf, e->d_entropy,
+                    e->d_stream_ncand, e->d_stream_endpos, e->d_ra_frame, e->d_ra_pose, e->d_ra_loss, e->d_ra_rot, e->d_ra_t,
+                    e->d_ra_correct, e->d_ra_steps, e->d_ra_imap, e->d_status, e->d_fragile, e->d_diffmaps, e->d_scores, e->d_sf, e->d_entropy,
                     e->d_avg, e->d_ref, e->d_inlier_map, e->d_steps_done, e->d_n_perm, e->d_loss, e->d_rot_err,
                     e->d_t_err, e->d_correct, e->d_frame_counter};
     for (void* p : ptrs)
@@ -191,6 +197,7 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
     CUC(cudaMalloc(&e->d_img_idx, n * H * 4 * sizeof(int32_t)));
     CUC(cudaMalloc(&e->d_cand_idx, n * H * sizeof(int32_t)));
     CUC(cudaMalloc(&e->d_stream_ncand, n * cfg->n_streams * sizeof(long long)));
+    CUC(cudaMalloc(&e->d_stream_endpos, n * cfg->n_streams * sizeof(unsigned long long)));
     CUC(cudaMalloc(&e->d_status, n * sizeof(uint32_t)));
     CUC(cudaMalloc(&e->d_fragile, sizeof(unsigned long long)));
     if (cfg->write_diffmaps) CUC(cudaMalloc(&e->d_diffmaps, n * H * N * sizeof(float)));
@@ -289,7 +296,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
         sp.seed = c.seed; sp.skip = c.stream_skip; sp.max_candidates = c.max_candidates;
         sp.frame0 = frame0;
         sp.hyp_pose = e->d_hyp_pose + o * Hh * 6; sp.hyp_P = e->d_hyp_P + o * Hh * 12; sp.img_idx = e->d_img_idx + o * Hh * 4; sp.cand_idx = e->d_cand_idx + o * Hh;
-        sp.stream_ncand = e->d_stream_ncand + o * c.n_streams; sp.status = e->d_status + o; sp.n_fragile = e->d_fragile;
+        sp.stream_ncand = e->d_stream_ncand + o * c.n_streams; sp.stream_endpos = e->d_stream_endpos + o * c.n_streams; sp.status = e->d_status + o; sp.n_fragile = e->d_fragile;
         sp.phase_cycles = e->d_phase;
         k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);
         e->launches++;
@@ -475,6 +482,147 @@ int dsac_forward(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coord
     }
     for (int c = 0; c < chunks; c++) CU(cudaStreamSynchronize(e->pipe[c]));
     if (out) sum_candidates(e, n, out);
+    return DSAC_OK;
+}
+
+int dsac_forward_dsac(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
+                      int32_t pix_shared, const double* gt_jp, int32_t random_draw, dsac_dsac_out* out) {
+    if (!e || !out) return DSAC_ERR_ARG;
+    if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
+    if (!coords || !pix) return fail(e, DSAC_ERR_ARG, "null input");
+    const dsac_config& c = e->cfg;
+    CU(cudaSetDevice(c.device));
+    cudaStream_t stream = e->pipe[0];
+    const size_t N = DSAC_N, nn = (size_t)n, H = c.n_hyps, jobs = nn * H, T = c.n_streams;
+    // refine-all buffers
+    if (jobs > e->ra_jobs) {
+        void* old[] = {e->d_ra_frame, e->d_ra_pose, e->d_ra_loss, e->d_ra_rot, e->d_ra_t, e->d_ra_correct, e->d_ra_steps};
+        for (void* q : old)
+            if (q) cudaFree(q);
+        e->d_ra_frame = nullptr; e->d_ra_pose = nullptr; e->d_ra_loss = nullptr; e->d_ra_rot = nullptr; e->d_ra_t = nullptr;
+        e->d_ra_correct = nullptr; e->d_ra_steps = nullptr;
+        e->ra_jobs = 0;
+        CU(cudaMalloc(&e->d_ra_frame, jobs * sizeof(int32_t)));
+        CU(cudaMalloc(&e->d_ra_pose, jobs * 6 * sizeof(double)));
+        CU(cudaMalloc(&e->d_ra_loss, jobs * sizeof(double)));
+        CU(cudaMalloc(&e->d_ra_rot, jobs * sizeof(double)));
+        CU(cudaMalloc(&e->d_ra_t, jobs * sizeof(double)));
+        CU(cudaMalloc(&e->d_ra_correct, jobs * sizeof(int32_t)));
+        CU(cudaMalloc(&e->d_ra_steps, jobs * sizeof(int32_t)));
+        std::vector<int32_t> jf(jobs);
+        for (size_t j = 0; j < jobs; j++) jf[j] = (int32_t)(j / H);
+        CU(cudaMemcpy(e->d_ra_frame, jf.data(), jobs * sizeof(int32_t), cudaMemcpyHostToDevice));
+        e->ra_jobs = jobs;
+    }
+    if (out->inlier_maps && jobs > e->ra_imap_jobs) {
+        if (e->d_ra_imap) cudaFree(e->d_ra_imap);
+        e->d_ra_imap = nullptr;
+        e->ra_imap_jobs = 0;
+        CU(cudaMalloc(&e->d_ra_imap, jobs * N * sizeof(int32_t)));
+        e->ra_imap_jobs = jobs;
+    }
+    CU(cudaMemcpyAsync(e->d_coords, coords, nn * N * 3 * sizeof(int16_t), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(e->d_pix, pix, (pix_shared ? 1 : nn) * N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    if (gt_jp) CU(cudaMemcpyAsync(e->d_gt, gt_jp, nn * 12 * sizeof(double), cudaMemcpyHostToDevice, stream));
+    e->cur_coords = e->d_coords; e->cur_pix = e->d_pix; e->cur_pix_shared = pix_shared; e->cur_gt = gt_jp ? e->d_gt : nullptr;
+    e->cur_n = 0;   // the soft-argmax backward does not apply to this pass
+    e->cur_frame0 = frame0;
+    const uint32_t saved = e->stages;
+    e->stages = DSAC_STAGE_SAMPLE | DSAC_STAGE_SCORE;
+    int rc = forward_range(e, 0, n, frame0, e->d_coords, e->d_pix, pix_shared, e->cur_gt, stream);
+    e->stages = saved;
+    if (rc != DSAC_OK) return rc;
+    {   // every hypothesis is a refinement job starting from its own pose (cnn.h:1155-1218)
+        RefineParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.coords = e->d_coords; rp.pix = e->d_pix; rp.pix_stride = pix_shared ? 0 : DSAC_N * 2;
+        rp.perm = e->d_perm;
+        rp.f = c.focal; rp.cx = c.cx; rp.cy = c.cy;
+        rp.thr = c.thr2d; rp.inlier_count = c.inlier_count; rp.ref_steps = c.ref_steps;
+        rp.n_jobs = (int)jobs;
+        rp.job_frame = e->d_ra_frame;
+        rp.job_init = e->d_hyp_pose;
+        rp.out_pose = e->d_ra_pose;
+        rp.steps_done = e->d_ra_steps;
+        rp.inlier_map = out->inlier_maps ? e->d_ra_imap : nullptr;
+        if (e->cur_gt) {
+            rp.gt_jp = e->cur_gt;
+            rp.loss = e->d_ra_loss; rp.rot_err = e->d_ra_rot; rp.t_err = e->d_ra_t; rp.correct = e->d_ra_correct;
+        }
+        k_refine<<<(unsigned)jobs, K4_THREADS, 0, stream>>>(rp);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    std::vector<double> sf(nn * H), loss(jobs, 0.0), rot(jobs, 0.0), terr(jobs, 0.0);
+    std::vector<int32_t> correct(jobs, 0), idx(nn * H * 4);
+    std::vector<unsigned long long> endpos(nn * T);
+    CU(cudaMemcpyAsync(sf.data(), e->d_sf, nn * H * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(idx.data(), e->d_img_idx, nn * H * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(endpos.data(), e->d_stream_endpos, nn * T * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    if (e->cur_gt) {
+        CU(cudaMemcpyAsync(loss.data(), e->d_ra_loss, jobs * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(rot.data(), e->d_ra_rot, jobs * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(terr.data(), e->d_ra_t, jobs * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(correct.data(), e->d_ra_correct, jobs * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    }
+#define D2H(dst, src, bytes)                                                                    \
+    do {                                                                                        \
+        if ((dst) && (src)) CU(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, stream)); \
+    } while (0)
+    D2H(out->hyp_pose, e->d_hyp_pose, nn * H * 6 * sizeof(double));
+    D2H(out->entropy, e->d_entropy, nn * sizeof(double));
+    D2H(out->ref_pose, e->d_ra_pose, jobs * 6 * sizeof(double));
+    D2H(out->steps_done, e->d_ra_steps, jobs * sizeof(int32_t));
+    D2H(out->inlier_maps, e->d_ra_imap, jobs * N * sizeof(int32_t));
+    D2H(out->status, e->d_status, nn * sizeof(uint32_t));
+#undef D2H
+    CU(cudaStreamSynchronize(stream));
+    if (out->sf) memcpy(out->sf, sf.data(), nn * H * sizeof(double));
+    if (out->img_idx) memcpy(out->img_idx, idx.data(), nn * H * 4 * sizeof(int32_t));
+    if (out->losses) memcpy(out->losses, loss.data(), jobs * sizeof(double));
+    for (size_t f = 0; f < nn; f++) {
+        const double* p = &sf[f * H];
+        // draw(), cnn.h:102-126
+        double probSum = 0, maxProb = -1;
+        int maxIdx = 0, pick = 0;
+        for (size_t i = 0; i < H; i++) {
+            if (p[i] < 1e-8) continue;
+            probSum += p[i];
+            if (maxProb < 0 || p[i] > maxProb) { maxProb = p[i]; maxIdx = (int)i; }
+        }
+        if (random_draw) {
+            // thread 0's generator continues after the sampling loop: same libstdc++ calls as drand (thread_rand.cpp:71-81)
+            std::mt19937 gen;
+            gen.seed(c.seed + (uint32_t)((frame0 + (long long)f) * (long long)T));
+            gen.discard(endpos[f * T]);
+            std::uniform_real_distribution<double> dist(0, probSum);
+            const double u = dist(gen);
+            double cum = 0;
+            bool found = false;
+            for (size_t i = 0; i < H; i++) {
+                if (p[i] < 1e-8) continue;
+                cum += p[i];
+                pick = (int)i;
+                if (cum > u) { found = true; break; }   // std::map::upper_bound on the cumulative sums
+            }
+            (void)found;
+        } else {
+            pick = maxIdx;
+        }
+        double expected = 0;
+        for (size_t h = 0; h < H; h++) expected += p[h] * loss[f * H + h];   // expectedMaxLoss, cnn.h:137-151
+        if (out->expected_loss) out->expected_loss[f] = expected;
+        if (out->hyp_idx) out->hyp_idx[f] = pick;
+        if (out->rot_err) out->rot_err[f] = rot[f * H + pick];
+        if (out->t_err) out->t_err[f] = terr[f * H + pick];
+        if (out->correct) out->correct[f] = correct[f * H + pick];
+        if (out->inlier_maps)   // the minimal set is excluded from its own inlier map (cnn.h:1221-1227)
+            for (size_t h = 0; h < H; h++)
+                for (int j = 0; j < 4; j++) {
+                    int cidx = idx[(f * H + h) * 4 + j];
+                    if (cidx >= 0) out->inlier_maps[(f * H + h) * N + cidx] = 0;
+                }
+    }
     return DSAC_OK;
 }
 

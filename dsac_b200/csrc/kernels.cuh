@@ -56,6 +56,7 @@ struct SampleParams {
     int32_t* img_idx;        // [n][H][4]
     int32_t* cand_idx;       // [n][H]
     long long* stream_ncand; // [n][T]
+    unsigned long long* stream_endpos;  // [n][T] stream words consumed when the stream's last hypothesis was accepted
     uint32_t* status;        // [n]
     unsigned long long* n_fragile;  // [1]
     unsigned long long* phase_cycles;  // [8] or null: thread-0 cycles per phase (development aid)
@@ -153,7 +154,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
     int h0, quota;
     stream_chunk(p.H, p.T, s, &h0, &quota);
     if (quota == 0) {
-        if (tid == 0) p.stream_ncand[(size_t)frame * p.T + s] = 0;
+        if (tid == 0) {
+            p.stream_ncand[(size_t)frame * p.T + s] = 0;
+            p.stream_endpos[(size_t)frame * p.T + s] = 0;
+        }
         return;
     }
 
@@ -334,9 +338,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
             long long cand = 0;
             double e2 = 1.7976931348623157e308, R[9], t[3];
             float obj[12], img[8];
-            int nsol = 0;
+            int nsol = 0, ci_keep = 0;
             if (qi < q_n) {
                 int ci = sm.q_idx[qi];
+                ci_keep = ci;
                 cand_parse_fast(sm.vals, sm.cand_start[ci], w_avail, cells);
                 cand = cand_base + ci;
                 P3PProblem pr;
@@ -379,7 +384,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
                 P[2] = make_float4((float)Rm[6], (float)Rm[7], (float)Rm[8], (float)tvec[2]);
                 *reinterpret_cast<int4*>(p.img_idx + hi * 4) = make_int4(cells[0], cells[1], cells[2], cells[3]);
                 p.cand_idx[hi] = (int32_t)cand;
-                if (rank == quota - 1) p.stream_ncand[(size_t)frame * p.T + s] = cand + 1;
+                if (rank == quota - 1) {
+                    p.stream_ncand[(size_t)frame * p.T + s] = cand + 1;
+                    p.stream_endpos[(size_t)frame * p.T + s] = (unsigned long long)pos + sm.cand_start[ci_keep + 1];
+                }
             }
             acc += tot;
         }
@@ -442,6 +450,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
         }
         if (tid == 0) {
             p.stream_ncand[(size_t)frame * p.T + s] = cand_base;
+            p.stream_endpos[(size_t)frame * p.T + s] = pos;
             atomicOr(p.status + frame, 1u /* DSAC_ST_SAMPLER_EXHAUSTED */);
         }
     }

@@ -20,7 +20,7 @@ ST_SAMPLER_EXHAUSTED, ST_REFINE_ABORTED = 1, 2
 EXPORTS = [
     "dsac_default_config", "dsac_engine_create", "dsac_engine_destroy", "dsac_last_error", "dsac_engine_config",
     "dsac_forward", "dsac_forward_device", "dsac_fetch", "dsac_device_view_get", "dsac_set_stages",
-    "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_kabsch", "dsac_stochastic_subsample",
+    "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_forward_dsac", "dsac_kabsch", "dsac_stochastic_subsample",
     "dsac_synth_frames", "dsac_version",
 ]
 
@@ -54,6 +54,14 @@ _BW_FIELDS = ["dloss_dobj", "dloss_dref", "dref_dhyp", "dref_dobj", "score_grads
 
 class BackwardOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in _BW_FIELDS]
+
+
+_DSAC_FIELDS = ["hyp_pose", "img_idx", "sf", "entropy", "ref_pose", "losses", "inlier_maps", "steps_done", "expected_loss",
+                "hyp_idx", "rot_err", "t_err", "correct", "status"]
+
+
+class DsacOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in _DSAC_FIELDS]
 
 
 SCORE_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
@@ -93,6 +101,8 @@ def load(build_if_missing=True):
     lib.dsac_set_score_hook.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dsac_backward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.POINTER(BackwardOut)]
+    lib.dsac_forward_dsac.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                      C.POINTER(DsacOut)]
     lib.dsac_kabsch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dsac_stochastic_subsample.argtypes = [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]
     lib.dsac_synth_frames.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_int64, C.c_int32, C.c_double, C.c_double,
@@ -160,6 +170,20 @@ class ForwardResult:
         self.status = np.zeros(n, np.uint32)
         self.raw = ForwardOut()
         for k in _OUT_FIELDS:
+            setattr(self.raw, k, _p(getattr(self, k)))
+
+
+class DsacResult:
+    """Host copies of the DSAC-variant processImage outputs (core/cnn.h:1028-1257)."""
+
+    def __init__(self, n, H, want_inlier_maps):
+        self.hyp_pose = np.zeros((n, H, 6)); self.img_idx = np.zeros((n, H, 4), np.int32); self.sf = np.zeros((n, H))
+        self.entropy = np.zeros(n); self.ref_pose = np.zeros((n, H, 6)); self.losses = np.zeros((n, H))
+        self.inlier_maps = np.zeros((n, H, N), np.int32) if want_inlier_maps else None
+        self.steps_done = np.zeros((n, H), np.int32); self.expected_loss = np.zeros(n); self.hyp_idx = np.zeros(n, np.int32)
+        self.rot_err = np.zeros(n); self.t_err = np.zeros(n); self.correct = np.zeros(n, np.int32); self.status = np.zeros(n, np.uint32)
+        self.raw = DsacOut()
+        for k in _DSAC_FIELDS:
             setattr(self.raw, k, _p(getattr(self, k)))
 
 
@@ -253,6 +277,18 @@ class Engine:
 
         self._hook = SCORE_HOOK(tramp)
         self._check(self.lib.dsac_set_score_hook(self.h, C.cast(self._hook, C.c_void_p), None))
+
+    def forward_dsac(self, coords, pix, gt_jp, random_draw=True, frame0=0, want_inlier_maps=False):
+        """dsac_forward_dsac: the DSAC / RANSAC variant (draw + refine all hypotheses + expected loss)."""
+        coords = np.ascontiguousarray(coords, np.int16).reshape(-1, N, 3)
+        n = coords.shape[0]
+        pix = np.ascontiguousarray(pix, np.int32)
+        shared = 1 if pix.size == N * 2 else 0
+        gt = np.ascontiguousarray(gt_jp, np.float64).reshape(n, 12) if gt_jp is not None else None
+        res = DsacResult(n, self.cfg.n_hyps, want_inlier_maps)
+        self._check(self.lib.dsac_forward_dsac(self.h, n, frame0, _p(coords), _p(pix), shared, _p(gt), int(random_draw),
+                                               C.byref(res.raw)))
+        return res
 
     def backward(self, coords, pix, gt_jp, full=True):
         coords = np.ascontiguousarray(coords, np.int16).reshape(-1, N, 3)

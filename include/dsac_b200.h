@@ -166,6 +166,29 @@ typedef struct dsac_backward_out {
 int dsac_backward(dsac_engine* e, int32_t n_frames, const int16_t* coords, const int32_t* pix, int32_t pix_shared,
                   const double* gt_jp, dsac_backward_out* out);
 
+/* Forward of the DSAC / RANSAC variant: processImage of core/cnn.h:1028-1257 -- same sampling and
+ * scoring, then draw() of the winning hypothesis (cnn.h:102-126), refinement of ALL hypotheses, per-hypothesis
+ * losses and the expectation of the loss (cnn.h:137-151).  random_draw != 0 draws with the stream-0 generator
+ * continuing after the sampler (pP.randomDraw, -rdraw), else arg-max.  Any output may be NULL. */
+typedef struct dsac_dsac_out {
+    double* hyp_pose;         /* [n][H][6]  hyps                     cnn.h:1042 */
+    int32_t* img_idx;         /* [n][H][4]  imgIdx                   cnn.h:1046 */
+    double* sf;               /* [n][H]     sfScores                 cnn.h:1048 */
+    double* entropy;          /* [n]        sfEntropy                cnn.h:1040 */
+    double* ref_pose;         /* [n][H][6]  refHyps                  cnn.h:1043 */
+    double* losses;           /* [n][H]     losses                   cnn.h:1052 */
+    int32_t* inlier_maps;     /* [n][H][N]  inlierMaps (support cells zeroed, cnn.h:1221-1227) */
+    int32_t* steps_done;      /* [n][H] */
+    double* expected_loss;    /* [n]        expectedLoss             cnn.h:1039 */
+    int32_t* hyp_idx;         /* [n]        hypIdx                   cnn.h:1057 */
+    double* rot_err;          /* [n]        of the drawn hypothesis  cnn.h:1056 */
+    double* t_err;            /* [n]                                 cnn.h:1055 */
+    int32_t* correct;         /* [n]                                 cnn.h:1041 */
+    uint32_t* status;         /* [n] */
+} dsac_dsac_out;
+int dsac_forward_dsac(dsac_engine* e, int32_t n_frames, int64_t frame0, const int16_t* coords, const int32_t* pix,
+                      int32_t pix_shared, const double* gt_jp, int32_t random_draw, dsac_dsac_out* out);
+
 /* Batched Kabsch (Hypothesis::calcRigidBodyTransform, Hypothesis.cpp:145-200):
  * for each of n problems with m correspondences, b ~ R a + t.  a,b: [n][m][3] doubles. */
 int dsac_kabsch(dsac_engine* e, int32_t n, int32_t m, const double* a, const double* b, double* R /* [n][9] */,

@@ -46,6 +46,15 @@ class ForwardOut(C.Structure):
     ]
 
 
+class DsacOut(C.Structure):
+    _fields_ = [
+        ("hyp_rvec", C.c_void_p), ("hyp_tvec", C.c_void_p), ("img_idx", C.c_void_p), ("sf", C.c_void_p),
+        ("ref_pose", C.c_void_p), ("losses", C.c_void_p), ("inlier_maps", C.c_void_p), ("steps_done", C.c_void_p),
+        ("entropy", C.c_double), ("expected_loss", C.c_double), ("rot_err", C.c_double), ("t_err", C.c_double),
+        ("hyp_idx", C.c_int32), ("correct", C.c_int32), ("stream0_endpos", C.c_uint64),
+    ]
+
+
 class BackwardOut(C.Structure):
     _fields_ = [
         ("dloss_dobj", C.c_void_p), ("dloss_dref", C.c_double * 6), ("dref_dobj", C.c_void_p),
@@ -299,6 +308,34 @@ def forward(cfg, coords, pix, gt_R=None, gt_t=None, want_diffmaps=True):
     gt = np.ascontiguousarray(gt_t, np.float64).reshape(3) if gt_t is not None else None
     out.status = lib().orc_forward(C.byref(cfg), _p(coords), _p(pix), _p(gR), _p(gt), C.byref(out.raw))
     out._keep = (coords, pix)
+    return out
+
+
+class ForwardDsac:
+    def __init__(self, cfg):
+        H = cfg.n_hyps
+        self.hyp_rvec = np.zeros((H, 3)); self.hyp_tvec = np.zeros((H, 3)); self.img_idx = np.zeros((H, 4), np.int32)
+        self.sf = np.zeros(H); self.ref_pose = np.zeros((H, 6)); self.losses = np.zeros(H)
+        self.inlier_maps = np.zeros((H, N), np.int32); self.steps_done = np.zeros(H, np.int32)
+        self.raw = DsacOut()
+        for k in ("hyp_rvec", "hyp_tvec", "img_idx", "sf", "ref_pose", "losses", "inlier_maps", "steps_done"):
+            setattr(self.raw, k, _p(getattr(self, k)))
+
+    def __getattr__(self, k):
+        raw = self.__dict__.get("raw")
+        if raw is not None and k in ("entropy", "expected_loss", "rot_err", "t_err", "hyp_idx", "correct", "stream0_endpos"):
+            return getattr(raw, k)
+        raise AttributeError(k)
+
+
+def forward_dsac(cfg, coords, pix, gt_R, gt_t, random_draw=True):
+    """DSAC / RANSAC variant (cnn.h processImage): draw + refine all hypotheses + expected loss."""
+    coords = np.ascontiguousarray(coords, np.int16).reshape(N, 3)
+    pix = np.ascontiguousarray(pix, np.int32).reshape(N, 2)
+    gR = np.ascontiguousarray(gt_R, np.float64).reshape(9)
+    gt = np.ascontiguousarray(gt_t, np.float64).reshape(3)
+    out = ForwardDsac(cfg)
+    out.status = lib().orc_forward_dsac(C.byref(cfg), int(random_draw), _p(coords), _p(pix), _p(gR), _p(gt), C.byref(out.raw))
     return out
 
 

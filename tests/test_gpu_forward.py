@@ -182,3 +182,27 @@ def test_score_hook_seam(engine_mod, oracle):
     assert np.abs(res.scores - ref.scores).max() <= 1e-5 * ref.scores.max()
     assert np.abs(res.avg_pose - ref.avg_pose).max() <= 1e-3
     assert np.array_equal(res.img_idx, ref.img_idx)
+
+
+@pytest.mark.parametrize("random_draw,T", [(True, 1), (False, 4)])
+def test_dsac_variant_forward_matches_oracle(engine_mod, oracle, random_draw, T):
+    """the DSAC / RANSAC variant's forward (core/cnn.h:1028-1257) -- draw, refinement of ALL hypotheses,
+    per-hypothesis losses, expected loss."""
+    E, O = engine_mod, oracle
+    nf, H = 2, 32
+    coords, pix, gt_cv, gt_jp = E.synth_frames(nf, n_streams=T)
+    eng = E.Engine(max_frames=nf, n_hyps=H, n_streams=T)
+    res = eng.forward_dsac(coords, pix, gt_jp, random_draw=random_draw, want_inlier_maps=True)
+    for f in range(nf):
+        cfg = O.default_config(seed=1305 + f * T, n_hyps=H, n_streams=T)
+        o = O.forward_dsac(cfg, coords[f], pix[f], gt_jp[f, :9], gt_jp[f, 9:], random_draw)
+        assert np.array_equal(o.img_idx, res.img_idx[f])
+        assert o.hyp_idx == res.hyp_idx[f]                       # same draw (same stream position, same libstdc++ calls)
+        assert np.array_equal(o.steps_done, res.steps_done[f])
+        assert np.array_equal(o.inlier_maps, res.inlier_maps[f])
+        assert np.abs(o.ref_pose[:, :3] - res.ref_pose[f][:, :3]).max() <= 1e-8
+        assert np.abs(o.ref_pose[:, 3:] - res.ref_pose[f][:, 3:]).max() <= 1e-5
+        assert np.abs(o.losses - res.losses[f]).max() <= 1e-6 * max(1.0, np.abs(o.losses).max())
+        assert np.abs(o.sf - res.sf[f]).max() <= 1e-4
+        assert abs(o.expected_loss - res.expected_loss[f]) <= 1e-3 * max(1.0, abs(o.expected_loss))
+        assert abs(o.rot_err - res.rot_err[f]) <= 1e-6 and abs(o.t_err - res.t_err[f]) <= 1e-4 and o.correct == res.correct[f]
