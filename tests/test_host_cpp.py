@@ -64,3 +64,16 @@ def test_train_driver_runs(apps, tmp_path):
     assert "Max gradient" in out.stdout
     log = np.loadtxt(tmp_path / "ransac_training_loss_train_obj.lua.txt")
     assert log.shape == (3, 3)
+
+
+@pytest.mark.gpu
+def test_dsac_variant_driver(apps, tmp_path):
+    """test_ransac (core/test_ransac.cpp) in synthetic mode, arg-max and random draw."""
+    for rdraw in ("0", "1"):
+        out = subprocess.run([os.path.join(apps, "test_ransac"), "-frames", "12", "-batch", "6", "-rI", "64", "-rdraw", rdraw],
+                             cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        errs = np.loadtxt(tmp_path / ("ransac_test_errors_obj_model_init.net_rdraw%s.txt" % rdraw))
+        summ = np.loadtxt(tmp_path / ("ransac_test_loss_obj_model_init.net_rdraw%s.txt" % rdraw))
+        assert errs.shape == (12, 11) and summ.shape == (7,)
+        assert summ[0] > 0.8 and np.isfinite(errs).all()
