@@ -206,3 +206,27 @@ def test_dsac_variant_forward_matches_oracle(engine_mod, oracle, random_draw, T)
         assert np.abs(o.sf - res.sf[f]).max() <= 1e-4
         assert abs(o.expected_loss - res.expected_loss[f]) <= 1e-3 * max(1.0, abs(o.expected_loss))
         assert abs(o.rot_err - res.rot_err[f]) <= 1e-6 and abs(o.t_err - res.t_err[f]) <= 1e-4 and o.correct == res.correct[f]
+
+
+def test_score_cnn_plugin_behind_the_seam(engine_mod, oracle):
+    """the reference's Score-CNN architecture as a zero-copy plug-in behind dsac_set_score_hook."""
+    import torch
+    from dsac_b200.score_cnn import ScoreCNN, MEAN
+    E, O = engine_mod, oracle
+    coords, pix, gt_cv, gt_jp = E.synth_frames(2)
+    H = 64
+    cnn = ScoreCNN(seed=3)
+    eng = E.Engine(max_frames=2, n_hyps=H)
+    eng.set_score_hook(cnn)
+    res = eng.forward(coords, pix, gt_jp, want_diffmaps=True)
+    plain = E.Engine(max_frames=2, n_hyps=H).forward(coords, pix, gt_jp)
+    assert np.array_equal(res.img_idx, plain.img_idx)            # sampling does not depend on the scorer
+    # scores = the same network evaluated on the fetched diffmaps
+    with torch.no_grad():
+        x = torch.from_numpy(res.diffmaps.reshape(-1, 1, 40, 40)).cuda() - MEAN
+        want = cnn.model(x).reshape(2, H).double().cpu().numpy()
+    assert np.abs(res.scores - want).max() <= 1e-4 * max(1.0, np.abs(want).max())
+    for f in range(2):
+        assert np.abs(O.softmax(res.scores[f]) - res.sf[f]).max() <= 1e-12
+        assert np.abs((res.sf[f][:, None] * res.hyp_pose[f]).sum(0) - res.avg_pose[f]).max() <= 1e-9 * 3000
+    assert np.isfinite(res.ref_pose).all()
