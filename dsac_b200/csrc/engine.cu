@@ -317,8 +317,17 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
         kp.alpha = c.alpha;
         kp.external_scores = 0;
         dim3 grid(kp.tiles_per_frame, n);
-        if (e->d_diffmaps) k_score<true><<<grid, K2_THREADS, 0, stream>>>(kp);
-        else k_score<false><<<grid, K2_THREADS, 0, stream>>>(kp);
+        static const int k2v = getenv("DSAC_K2_VARIANT") ? atoi(getenv("DSAC_K2_VARIANT")) : 0;   // experiment switch
+        const bool dmw = e->d_diffmaps != nullptr;
+#define K2_LAUNCH(KERN) do { if (dmw) KERN<<<grid, K2_THREADS, 0, stream>>>(kp); else KERN<<<grid, K2_THREADS, 0, stream>>>(kp); } while (0)
+        switch (k2v) {
+            case 1: if (dmw) k_score<true, true><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score<false, true><<<grid, K2_THREADS, 0, stream>>>(kp); break;
+            case 2: if (dmw) k_score2<true, 0><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score2<false, 0><<<grid, K2_THREADS, 0, stream>>>(kp); break;
+            case 3: if (dmw) k_score2<true, 1><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score2<false, 1><<<grid, K2_THREADS, 0, stream>>>(kp); break;
+            case 4: if (dmw) k_score2<true, 2><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score2<false, 2><<<grid, K2_THREADS, 0, stream>>>(kp); break;
+            default: if (dmw) k_score<true, false><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score<false, false><<<grid, K2_THREADS, 0, stream>>>(kp); break;
+        }
+#undef K2_LAUNCH
         e->launches++;
         CU(cudaGetLastError());
         if (e->hook) {

@@ -92,6 +92,12 @@ DSAC_HD void project_point(const double R[9], const double t[3], double X, doubl
 
 // ----------------------------------------------------------------------------- P3P
 // Largest real root of y^3 + a2 y^2 + a1 y + a0 (the resolvent cubic of Ferrari's method).
+#if defined(__CUDA_ARCH__)
+#define DSAC_RSQRTF_EARLY(x) rsqrtf(x)
+#else
+#define DSAC_RSQRTF_EARLY(x) (1.0f / sqrtf(x))
+#endif
+
 DSAC_HD double cubic_first_root(double a2, double a1, double a0) {
     double Q = (3 * a1 - a2 * a2) / 9;
     double R = (9 * a2 * a1 - 27 * a0 - 2 * a2 * a2 * a2) / 54;
@@ -158,12 +164,48 @@ DSAC_HD double rsqrt_or(double x) {
 // quartic_roots with an "uncertain" verdict: set when any sign decision of Ferrari's method lies
 // within a relative band of 1e-9 (>= 10^6 x double rounding), i.e. when another instance of the same
 // computation with different rounding could decide differently.  Used by the conservative filter.
+// The same root of the resolvent cubic as cubic_first_root (the largest one when there are three), for the
+// conservative filter only: an fp32 closed-form seed (a handful of MUFU operations instead of fp64
+// acos/cos/cbrt/sqrt, ~300 instructions) restored to fp64 accuracy by Newton steps on the cubic.  *ok is false
+// when the last step has not collapsed below 1e-9 of the problem's scale (near-double root, overflow, NaN) and
+// the caller must then treat the candidate as uncertain.
+DSAC_HD double cubic_first_root_seeded(double a2, double a1, double a0, bool* ok) {
+    const double Q = (3 * a1 - a2 * a2) * (1.0 / 9), R = (9 * a2 * a1 - 27 * a0 - 2 * a2 * a2 * a2) * (1.0 / 54);
+    const double Q3 = Q * Q * Q, D = Q3 + R * R, sh = a2 * (1.0 / 3);
+    const float Qf = (float)Q, Rf = (float)R;
+    float s;
+    if (D <= 0) {
+        float cs = Rf * DSAC_RSQRTF_EARLY(-(float)Q3);
+        cs = fminf(1.f, fmaxf(-1.f, cs));
+#if defined(__CUDA_ARCH__)
+        s = 2.f * sqrtf(-Qf) * __cosf(acosf(cs) * (1.f / 3));
+#else
+        s = 2.f * sqrtf(-Qf) * cosf(acosf(cs) * (1.f / 3));
+#endif
+    } else {
+        float AD = cbrtf(fabsf(Rf) + sqrtf((float)D));
+        AD = (Rf >= 0) ? AD : -AD;
+        s = AD + ((AD == 0) ? 0.f : -Qf / AD);
+    }
+    double y = (double)s - sh, dy = 0;
+#pragma unroll
+    for (int it = 0; it < 3; it++) {
+        const double g = ((y + a2) * y + a1) * y + a0, gp = (3 * y + 2 * a2) * y + a1;
+        dy = g / gp;
+        y -= dy;
+    }
+    *ok = fabs(dy) <= 1e-9 * (fabs(y) + fabs(sh));
+    return y;
+}
+
 DSAC_HD int quartic_roots_banded(double a, double b, double c, double d, double e, double x[4], bool* uncertain) {
     const double TOL = 1e-9;
     *uncertain = false;
     double ia = 1.0 / a;
     b *= ia; c *= ia; d *= ia; e *= ia;
-    double y1 = cubic_first_root(-c, d * b - 4 * e, 4 * c * e - d * d - b * b * e);
+    bool cubic_ok;
+    double y1 = cubic_first_root_seeded(-c, d * b - 4 * e, 4 * c * e - d * d - b * b * e, &cubic_ok);
+    if (!cubic_ok) { *uncertain = true; return 0; }
     double R2 = 0.25 * b * b - c + y1, mR = 0.25 * b * b + fabs(c) + fabs(y1);
     if (!(fabs(R2) > TOL * mR)) { *uncertain = true; return 0; }   // also catches NaN and the R ~ 0 branch
     if (R2 < 0) return 0;
