@@ -18,7 +18,8 @@ SOURCES = ["engine.cu", "host_util.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
-    "-Xcompiler", "-O2", "-DDSAC_BUILD=1", "-DK1_THREADS_DEF=" + os.environ.get("DSAC_K1_THREADS", "256"),
+    "-Xcompiler", "-O2", "-DDSAC_BUILD=1", "-DK1_THREADS_DEF=" + os.environ.get("DSAC_K1_THREADS", "384"),
+    *(["-DK1_MIN_BLOCKS=" + os.environ["DSAC_K1_MIN_BLOCKS"]] if "DSAC_K1_MIN_BLOCKS" in os.environ else []),
 ]
 
 

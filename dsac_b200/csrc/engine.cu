@@ -298,6 +298,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
         sp.hyp_pose = e->d_hyp_pose + o * Hh * 6; sp.hyp_P = e->d_hyp_P + o * Hh * 12; sp.img_idx = e->d_img_idx + o * Hh * 4; sp.cand_idx = e->d_cand_idx + o * Hh;
         sp.stream_ncand = e->d_stream_ncand + o * c.n_streams; sp.stream_endpos = e->d_stream_endpos + o * c.n_streams; sp.status = e->d_status + o; sp.n_fragile = e->d_fragile;
         sp.phase_cycles = e->d_phase;
+        { const char* g = getenv("DSAC_K1_A2_GENERIC"); sp.a2_generic = (g && g[0] == '1') ? 1 : 0; }
         k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);
         e->launches++;
         CU(cudaGetLastError());

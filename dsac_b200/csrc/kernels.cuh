@@ -60,27 +60,30 @@ struct SampleParams {
     uint32_t* status;        // [n]
     unsigned long long* n_fragile;  // [1]
     unsigned long long* phase_cycles;  // [8] or null: thread-0 cycles per phase (development aid)
+    int a2_generic;                    // 1: always take the general boundary path (test aid, DSAC_K1_A2_GENERIC=1)
 };
 
 #ifndef K1_THREADS_DEF
-#define K1_THREADS_DEF 256
+#define K1_THREADS_DEF 384
 #endif
 constexpr int K1_THREADS = K1_THREADS_DEF;
 constexpr int K1_WARPS = K1_THREADS / 32;
 #ifndef K1_MIN_BLOCKS
-#define K1_MIN_BLOCKS (512 / K1_THREADS_DEF)
+#define K1_MIN_BLOCKS 2
 #endif
-constexpr int K1_SUPER_MAX = 16;                          // x256 candidates per super-round
+constexpr int K1_SUPER_MAX = 4096 / K1_THREADS;           // super-round = up to 4096 candidates (phase C packs them in 128 flag words)
 constexpr int K1_CANDS = K1_SUPER_MAX * K1_THREADS;       // candidates buffered per super-round
 constexpr int K1_WORDS = K1_CANDS * 8 + 1024;             // decoded stream words buffered per super-round
 constexpr int K1_WAVE = MT_N - MT_M;                      // 227 new MT19937 words per barrier
+constexpr int K1_EV_CAP = 64;                             // repeated-pair events buffered per warp and super-round (expected: ~4)
+constexpr int K1_BRK_CAP = 160;                           // candidates with a repeated cell per super-round (expected: ~16)
 
 // Per-cell record staged in shared memory: scene coordinate (mm) and the float-rounded
 // normalised pixel that cv::undistortPoints hands to P3P.
-struct __align__(4) CellRec {
-    short X, Y, Z;   // scene coordinate, mm
-    short u, v;      // sampling pixel
-    short pad;
+struct __align__(8) CellRec {
+    short X, Y, Z, pad;   // scene coordinate, mm
+    float xn, yn;         // normalised pixel rounded to float (cv::undistortPoints), see p3p_pixel
+    double k;             // 1 / |(u, v, 1)| of the bearing P3P derives from it (used by the filter only)
 };
 
 struct K1Smem {
@@ -94,6 +97,12 @@ struct K1Smem {
     int warp[2][K1_WARPS];
     uint32_t newpos;
     int q_n, n_sr, any_reject, walk_fail;
+    // event-based boundary phase: repeated (x, y) pairs found by each warp in its segment of the window, and the
+    // resulting breaks of the 8-words-per-candidate rhythm
+    uint32_t ev[K1_WARPS][K1_EV_CAP];           // (pair index << 2) | distance to the equal predecessor (1..3)
+    int ev_n[K1_WARPS];
+    unsigned short brk_ci[K1_BRK_CAP], brk_cur[K1_BRK_CAP];   // from candidate brk_ci on, candidates start at pair brk_cur + 4*(i - brk_ci)
+    int brk_n;
 };
 
 // 4 distinct cells (x, y drawn in that order, a repeated cell is re-drawn: cnn_softam.h:1021-1039)
@@ -166,11 +175,16 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
 
     const int16_t* coords = p.coords + (size_t)frame * DSAC_N_CONST * 3;
     const int32_t* pix = p.pix + (size_t)frame * p.pix_stride;
+    const double k1_inv_f = 1. / p.f, k1_cx_f = p.cx * k1_inv_f, k1_cy_f = p.cy * k1_inv_f;
     {
         for (int c = tid; c < DSAC_N_CONST; c += K1_THREADS) {
             CellRec r;
-            r.X = __ldg(coords + c * 3); r.Y = __ldg(coords + c * 3 + 1); r.Z = __ldg(coords + c * 3 + 2);
-            r.u = (short)__ldg(pix + c * 2); r.v = (short)__ldg(pix + c * 2 + 1); r.pad = 0;
+            r.X = __ldg(coords + c * 3); r.Y = __ldg(coords + c * 3 + 1); r.Z = __ldg(coords + c * 3 + 2); r.pad = 0;
+            r.xn = (float)(((double)__ldg(pix + c * 2) - p.cx) * k1_inv_f);       // cv::undistortPoints rounds to float (p3p_pixel)
+            r.yn = (float)(((double)__ldg(pix + c * 2 + 1) - p.cy) * k1_inv_f);
+            const double mu = r.xn * p.f + p.cx, mv = r.yn * p.f + p.cy;        // float * double
+            const double u = k1_inv_f * mu - k1_cx_f, v = k1_inv_f * mv - k1_cy_f;
+            r.k = rsqrt(u * u + v * v + 1);
             sm.cell[c] = r;
         }
     }
@@ -184,17 +198,31 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
     const long long cand_max = p.max_candidates > 0 ? (long long)p.max_candidates : (1ll << 40);
     int S = 4;                              // x256 candidates in the next super-round (adapted to the acceptance rate)
 
-    const double k1_inv_f = 1. / p.f;
     auto load_problem = [&](const int cells[4], P3PProblem& pr) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const CellRec r = sm.cell[cells[j]];
-            const float xn = (float)(((double)r.u - p.cx) * k1_inv_f);   // cv::undistortPoints rounds to float (p3p_pixel)
-            const float yn = (float)(((double)r.v - p.cy) * k1_inv_f);
-            pr.mu[j] = xn * p.f + p.cx;   // float * double
-            pr.mv[j] = yn * p.f + p.cy;
+            pr.mu[j] = r.xn * p.f + p.cx;   // float * double
+            pr.mv[j] = r.yn * p.f + p.cy;
             pr.X[j][0] = (double)r.X; pr.X[j][1] = (double)r.Y; pr.X[j][2] = (double)r.Z;
         }
+    };
+    // the filter's inputs straight from the cell table: bearings of points 0..2 from the stored 1/|(u, v, 1)|
+    auto filter_candidate = [&](const int cells[4]) -> bool {
+        double bear[3][3], X[4][3], mu3 = 0, mv3 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const CellRec r = sm.cell[cells[j]];
+            const double mu = r.xn * p.f + p.cx, mv = r.yn * p.f + p.cy;
+            X[j][0] = (double)r.X; X[j][1] = (double)r.Y; X[j][2] = (double)r.Z;
+            if (j < 3) {
+                const double u = k1_inv_f * mu - k1_cx_f, v = k1_inv_f * mv - k1_cy_f;
+                bear[j][0] = u * r.k; bear[j][1] = v * r.k; bear[j][2] = r.k;
+            } else {
+                mu3 = mu; mv3 = mv;
+            }
+        }
+        return p3p_quick_core(bear, X, mu3, mv3, p.f, p.cx, p.cy, (double)p.thr);
     };
 
     long long tA1 = 0, tA2 = 0, tB = 0, tC = 0, tD = 0, tE = 0, tmark = clock64();
@@ -225,12 +253,83 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
         const int w_avail = min((int)(gen - pos), K1_WORDS);
         K1_MARK(tA1);
 
-        // ---------------- phase A2: candidate boundaries.  A candidate is 8 words long unless a cell repeats
-        // (+2 words) or a draw is rejected (+1).  Per chunk of 256 candidates (one per thread), the starts
-        // 8*tid + (extra words of earlier candidates) are iterated to a fixed point -- one pass when the chunk
-        // has no repeat (39 %), else typically 2-3 cheap passes; at the fixed point candidate 0 is exact,
-        // hence candidate 1, and so on.
-        {
+        // ---------------- phase A2: candidate boundaries.  A candidate is 8 words (4 (x, y) pairs) long unless a cell
+        // repeats (+2 words) or a draw is rejected (+1).  Fast path (no rejected draw in the window): every warp scans
+        // a segment of the window for pairs equal to one of their three predecessors -- the only way four consecutive
+        // pairs can fail to be distinct -- (~30 events per super-round); thread 0 walks the events in order, parses the
+        // few candidates that really contain a repeat with the generic parser, and records where the 4-pair rhythm
+        // breaks; every thread then derives its candidates' starts from the break list.  Three barriers per
+        // super-round.  Windows with a rejected draw (one per ~2000 frames) or an overflowing list take the
+        // general fixed-point path below.
+        bool a2_done = false;
+        if (!sm.any_reject && !p.a2_generic) {
+            const unsigned short* pr16 = reinterpret_cast<const unsigned short*>(sm.vals);
+            const int scan_end = min(w_avail >> 1, n_target * 4 + 384);
+            const int warp_id = tid >> 5;
+            const int seg = (((scan_end + K1_WARPS - 1) / K1_WARPS) + 31) & ~31;
+            const int wbeg = warp_id * seg, wend = min(wbeg + seg, scan_end);
+            int cnt = 0;
+            for (int k0 = wbeg; k0 < wend; k0 += 32) {
+                const int k = k0 + lane;
+                unsigned d = 0;
+                if (k < wend) {
+                    const unsigned pk = pr16[k];
+                    const unsigned p1 = (k >= 1) ? pr16[k - 1] : 0xffffu, p2 = (k >= 2) ? pr16[k - 2] : 0xffffu,
+                                   p3 = (k >= 3) ? pr16[k - 3] : 0xffffu;
+                    d = (pk == p1) ? 1u : (pk == p2) ? 2u : (pk == p3) ? 3u : 0u;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, d != 0);
+                if (d) {
+                    const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (slot < K1_EV_CAP) sm.ev[warp_id][slot] = ((uint32_t)k << 2) | d;
+                }
+                cnt += __popc(m);
+            }
+            if (lane == 0) sm.ev_n[warp_id] = cnt;
+            __syncthreads();
+            if (tid == 0) {
+                int cur = 0, ci = 0, nb = 1, stop_at = -1;
+                bool fail = false;
+                sm.brk_ci[0] = 0; sm.brk_cur[0] = 0;
+                for (int w = 0; w < K1_WARPS && !fail && stop_at < 0; w++) {
+                    const int n = sm.ev_n[w];
+                    if (n > K1_EV_CAP) { fail = true; break; }
+                    for (int e = 0; e < n; e++) {
+                        const uint32_t evv = sm.ev[w][e];
+                        const int k = (int)(evv >> 2), d = (int)(evv & 3u);
+                        if (k < cur) continue;                 // inside a candidate already parsed
+                        const int j = (k - cur) >> 2, sp = cur + 4 * j;
+                        if (k - d < sp) continue;              // the equal pair belongs to the previous candidate
+                        if (ci + j >= n_target) { stop_at = n_target; break; }
+                        int cells[4];
+                        const int q = cand_parse(sm.vals, 2 * sp, 2 * scan_end, cells);
+                        if (q < 0) { stop_at = ci + j; break; }   // window ends inside this candidate
+                        if ((q & 1) || nb >= K1_BRK_CAP) { fail = true; break; }
+                        ci += j + 1;
+                        cur = q >> 1;
+                        sm.brk_ci[nb] = (unsigned short)ci;
+                        sm.brk_cur[nb] = (unsigned short)cur;
+                        nb++;
+                    }
+                }
+                int n_ok = ci + ((scan_end - cur) >> 2);       // clean 4-pair candidates after the last break
+                if (stop_at >= 0) n_ok = min(n_ok, stop_at);
+                sm.n_sr = min(n_ok, n_target);
+                sm.brk_n = nb;
+                sm.walk_fail = fail ? 1 : 0;
+            }
+            __syncthreads();
+            if (!sm.walk_fail) {
+                const int n_ok = sm.n_sr, nb = sm.brk_n;
+                int m = 0;
+                for (int i = tid; i <= n_ok; i += K1_THREADS) {
+                    while (m + 1 < nb && (int)sm.brk_ci[m + 1] <= i) m++;
+                    sm.cand_start[i] = (unsigned short)(2 * ((int)sm.brk_cur[m] + 4 * (i - (int)sm.brk_ci[m])));
+                }
+                a2_done = true;
+            }
+        }
+        if (!a2_done) {
             int rp = 0, n_done = 0, par = 0;   // word offset of the chunk, candidates placed so far
             bool out_of_words = false;
             while (n_done < n_target && !out_of_words) {
@@ -281,9 +380,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
             if (i < n_sr) {
                 int cells[4];
                 cand_parse_fast(sm.vals, sm.cand_start[i], w_avail, cells);
-                P3PProblem pr;
-                load_problem(cells, pr);
-                need = minimal_set_needs_full_pr(pr, p.f, p.cx, p.cy, p.thr);
+                need = filter_candidate(cells);
             }
             uint32_t bits = __ballot_sync(0xffffffffu, need);
             if (lane == 0) sm.flagbits[i >> 5] = bits;

@@ -24,6 +24,13 @@
 #define DSAC_GRID_CONST 40  /* CNN_OBJ_PATCHSIZE, lua_calls.h:33 */
 #define DSAC_N_CONST 1600
 #define DSAC_MAXINPUT_F 100.0f  /* CNN_OBJ_MAXINPUT, lua_calls.h:36 */
+// Width (px) of the conservative filter's band above the acceptance threshold: a candidate is "certainly
+// rejected" only if every P3P root puts the 4th point farther than thr + band.  The filter and the exact check
+// differ by fp64 noise (amplified at most 1e4x by the conditioning guards) plus the reference's float rounding
+// of pixels and projections (6e-5 px at 640 px), so 0.05 px leaves a margin of ~10^3.
+#ifndef DSAC_FILTER_BAND_PX
+#define DSAC_FILTER_BAND_PX 0.05
+#endif
 
 namespace dsac {
 
@@ -464,7 +471,7 @@ DSAC_HDN bool p3p_quick_needs_full(const P3PProblem& pr, const P3PFront& fr, dou
     double e2x = e3y * e1z - e3z * e1y, e2y = e3z * e1x - e3x * e1z, e2z = e3x * e1y - e3y * e1x;
     double wx = pr.X[3][0] - pr.X[0][0], wy = pr.X[3][1] - pr.X[0][1], wz = pr.X[3][2] - pr.X[0][2];
     double al = wx * e1x + wy * e1y + wz * e1z, be = wx * e2x + wy * e2y + wz * e2z, ga = wx * e3x + wy * e3y + wz * e3z;
-    const double lim2 = (thr + 1.0) * (thr + 1.0);
+    const double lim2 = (thr + DSAC_FILTER_BAND_PX) * (thr + DSAC_FILTER_BAND_PX);
     for (int i = 0; i < fr.nroots; i++) {
         double x0 = fr.xr[i];
         if (!(x0 == x0)) return true;
@@ -574,32 +581,30 @@ DSAC_HDN bool minimal_set_hypothesis(const float obj[12], const float img[8], do
 // Self-contained (fully inlined, register-resident) version of the conservative filter: same contract as
 // p3p_quick_needs_full, but it does not share the front end with the full solve, so every decision the
 // front end takes (degeneracy tests, existence of real roots) is protected by a tolerance band instead.
-DSAC_HD bool p3p_quick_inline(const P3PProblem& pr, double f, double cx, double cy, double inv_f, double thr) {
-    const double cx_f = cx * inv_f, cy_f = cy * inv_f;
-    double bear[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        double u = inv_f * pr.mu[i] - cx_f, v = inv_f * pr.mv[i] - cy_f;
-#if defined(__CUDA_ARCH__)
-        double k = rsqrt(u * u + v * v + 1);
+// DSAC_FLAG(k): "needs the full solve", k = which guard fired (counted only in the host statistics build)
+#if defined(DSAC_FILTER_STATS) && !defined(__CUDA_ARCH__)
+static long long g_filter_reason[24];
+#define DSAC_FLAG(k) (g_filter_reason[k]++, true)
 #else
-        double k = 1. / sqrt(u * u + v * v + 1);
+#define DSAC_FLAG(k) true
 #endif
-        bear[i][0] = u * k; bear[i][1] = v * k; bear[i][2] = k;
-    }
-    const double ax = pr.X[1][0] - pr.X[0][0], ay = pr.X[1][1] - pr.X[0][1], az = pr.X[1][2] - pr.X[0][2];
-    const double bx = pr.X[2][0] - pr.X[0][0], by = pr.X[2][1] - pr.X[0][1], bz = pr.X[2][2] - pr.X[0][2];
-    const double gx = pr.X[2][0] - pr.X[1][0], gy = pr.X[2][1] - pr.X[1][1], gz = pr.X[2][2] - pr.X[1][2];
+// Core of the filter on prepared inputs: unit bearings of points 0..2, the four scene coordinates and the pixel
+// (mu3, mv3) of the 4th point as P3P sees it (k_sample keeps 1/|(u, v, 1)| per cell in shared memory).
+DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], double mu3, double mv3, double f, double cx,
+                            double cy, double thr) {
+    const double ax = X[1][0] - X[0][0], ay = X[1][1] - X[0][1], az = X[1][2] - X[0][2];
+    const double bx = X[2][0] - X[0][0], by = X[2][1] - X[0][1], bz = X[2][2] - X[0][2];
+    const double gx = X[2][0] - X[1][0], gy = X[2][1] - X[1][1], gz = X[2][2] - X[1][2];
     const double s01 = ax * ax + ay * ay + az * az, s02 = bx * bx + by * by + bz * bz, s12 = gx * gx + gy * gy + gz * gz;
     const double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
     const double nn = nx * nx + ny * ny + nz * nz;
-    if (!(s01 > 0) || !(nn > 0)) return true;
+    if (!(s01 > 0) || !(nn > 0)) return DSAC_FLAG(1);
     const double p = 2 * (bear[1][0] * bear[2][0] + bear[1][1] * bear[2][1] + bear[1][2] * bear[2][2]);
     const double q = 2 * (bear[0][0] * bear[2][0] + bear[0][1] * bear[2][1] + bear[0][2] * bear[2][2]);
     const double r = 2 * (bear[0][0] * bear[1][0] + bear[0][1] * bear[1][1] + bear[0][2] * bear[1][2]);
     const double inv_c2 = 1.0 / s01;
     const double a = inv_c2 * s12, b = inv_c2 * s02;
-    if (!(fabs(p * p + q * q + r * r - p * q * r - 1) > 1e-12)) return true;
+    if (!(fabs(p * p + q * q + r * r - p * q * r - 1) > 1e-12)) return DSAC_FLAG(2);
     const double N2 = 1 - a - b, N1 = q * (a - 1), N0 = 1 - a + b;
     const double D1 = b * r, D0 = -b * p;
     double xr[4];
@@ -612,10 +617,10 @@ DSAC_HD bool p3p_quick_inline(const P3PProblem& pr, double f, double cx, double 
         const double c2 = F2 * DD0 + F1 * DD1 + DD2 - b * (2 * N2 * N0 + N1 * N1) - br * (N1 * D0 + N0 * D1);
         const double c1 = F1 * DD0 + DD1 - b * (2 * N1 * N0) - br * (N0 * D0);
         const double c0 = DD0 - b * (N0 * N0);
-        if (!(fabs(c4) > 1e-12 * (fabs(c3) + fabs(c2) + fabs(c1) + fabs(c0)))) return true;
+        if (!(fabs(c4) > 1e-12 * (fabs(c3) + fabs(c2) + fabs(c1) + fabs(c0)))) return DSAC_FLAG(3);
         bool uncertain;
         nroots = quartic_roots_banded(c4, c3, c2, c1, c0, xr, &uncertain);
-        if (uncertain) return true;
+        if (uncertain) return DSAC_FLAG(4);
     }
     if (nroots == 0) return false;   // no real root, by a margin no rounding can bridge
     // world triangle frame and the 4th point's coordinates in it
@@ -623,14 +628,14 @@ DSAC_HD bool p3p_quick_inline(const P3PProblem& pr, double f, double cx, double 
     const double e1x = ax * inv_d, e1y = ay * inv_d, e1z = az * inv_d;
     const double e3x = nx * inv_n, e3y = ny * inv_n, e3z = nz * inv_n;
     const double e2x = e3y * e1z - e3z * e1y, e2y = e3z * e1x - e3x * e1z, e2z = e3x * e1y - e3y * e1x;
-    const double wx = pr.X[3][0] - pr.X[0][0], wy = pr.X[3][1] - pr.X[0][1], wz = pr.X[3][2] - pr.X[0][2];
+    const double wx = X[3][0] - X[0][0], wy = X[3][1] - X[0][1], wz = X[3][2] - X[0][2];
     const double al = wx * e1x + wy * e1y + wz * e1z, be = wx * e2x + wy * e2y + wz * e2z, ga = wx * e3x + wy * e3y + wz * e3z;
-    const double lim2 = (thr + 1.0) * (thr + 1.0);
+    const double lim2 = (thr + DSAC_FILTER_BAND_PX) * (thr + DSAC_FILTER_BAND_PX);
     for (int i = 0; i < 4; i++) {
         if (i >= nroots) break;
         double x = xr[i];
         const double Dn = D1 * x + D0;
-        if (!(fabs(Dn) > 2e-3 * (fabs(D1 * x) + fabs(D0)))) return true;   // (the full solve switches formula at 1e-3)
+        if (!(fabs(Dn) > 1.1e-3 * (fabs(D1 * x) + fabs(D0)))) return DSAC_FLAG(5);   // (the full solve switches formula at 1e-3)
         double y = -((N2 * x + N1) * x + N0) / Dn;
         const double f1 = (1 - a) * y * y - a * x * x - p * y + a * r * x * y + 1;
         const double f2 = (1 - b) * x * x - b * y * y - q * x + b * r * x * y + 1;
@@ -638,16 +643,16 @@ DSAC_HD bool p3p_quick_inline(const P3PProblem& pr, double f, double cx, double 
         const double j21 = 2 * (1 - b) * x - q + b * r * y, j22 = -2 * b * y + b * r * x;
         const double det = j11 * j22 - j12 * j21;
         const double jn = j11 * j11 + j12 * j12 + j21 * j21 + j22 * j22;
-        if (!(fabs(det) > 1e-4 * jn)) return true;
+        if (!(fabs(det) > 1e-4 * jn)) return DSAC_FLAG(6);
         const double idet = 1.0 / det;
         const double dx = (f1 * j22 - f2 * j12) * idet, dy = (j11 * f2 - j21 * f1) * idet;
         x -= dx;
         y -= dy;
-        if (!(fabs(dx) + fabs(dy) <= 1e-6 * (fabs(x) + fabs(y)))) return true;
+        if (!(fabs(dx) + fabs(dy) <= 1e-6 * (fabs(x) + fabs(y)))) return DSAC_FLAG(7);
         if (x < -1e-6 || y < -1e-6) continue;
-        if (x < 1e-6 || y < 1e-6) return true;
+        if (x < 1e-6 || y < 1e-6) return DSAC_FLAG(8);
         const double v = x * x + y * y - x * y * r;
-        if (!(v > 1e-12)) return true;
+        if (!(v > 1e-12)) return DSAC_FLAG(9);
         const double Z = d01 * rsqrt_or(v);
         const double L0 = x * Z, L1 = y * Z;
         const double M0x = L0 * bear[0][0], M0y = L0 * bear[0][1], M0z = L0 * bear[0][2];
@@ -661,11 +666,27 @@ DSAC_HD bool p3p_quick_inline(const P3PProblem& pr, double f, double cx, double 
         const double Y3 = M0y + al * c1y + be * c2y + ga * c3y;
         const double Z3 = M0z + al * c1z + be * c2z + ga * c3z;
         const double iz = 1.0 / Z3;
-        const double du = cx + f * X3 * iz - pr.mu[3], dv = cy + f * Y3 * iz - pr.mv[3];
+        const double du = cx + f * X3 * iz - mu3, dv = cy + f * Y3 * iz - mv3;
         const double e2 = du * du + dv * dv;
-        if (!(e2 > lim2)) return true;
+        if (!(e2 > lim2)) return DSAC_FLAG(10);
     }
     return false;
+}
+
+DSAC_HD bool p3p_quick_inline(const P3PProblem& pr, double f, double cx, double cy, double inv_f, double thr) {
+    const double cx_f = cx * inv_f, cy_f = cy * inv_f;
+    double bear[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double u = inv_f * pr.mu[i] - cx_f, v = inv_f * pr.mv[i] - cy_f;
+#if defined(__CUDA_ARCH__)
+        double k = rsqrt(u * u + v * v + 1);
+#else
+        double k = 1. / sqrt(u * u + v * v + 1);
+#endif
+        bear[i][0] = u * k; bear[i][1] = v * k; bear[i][2] = k;
+    }
+    return p3p_quick_core(bear, pr.X, pr.mu[3], pr.mv[3], f, cx, cy, thr);
 }
 
 // ---------------------------------------------------------------------------------------

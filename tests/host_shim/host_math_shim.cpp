@@ -103,3 +103,12 @@ extern "C" void shim_filter_stats(const int16_t* coords, const int32_t* pix, uin
         out[5] += (acc && !q32);
     }
 }
+
+// guard counters of the fp64 conservative filter (only with -DDSAC_FILTER_STATS)
+extern "C" void shim_filter_reasons(long long out[24]) {
+#ifdef DSAC_FILTER_STATS
+    for (int k = 0; k < 24; k++) out[k] = dsac::g_filter_reason[k];
+#else
+    for (int k = 0; k < 24; k++) out[k] = -1;
+#endif
+}

@@ -71,3 +71,22 @@ def test_stream_chunk_partition(host_shim):
             q, r = divmod(H, T)
             assert cnt.value == q + (1 if s < r else 0)
         assert covered == list(range(H))
+
+
+def test_conservative_filter_never_rejects_an_accepted_candidate(host_shim, engine_mod):
+    """K1's fp64 filter (p3p_quick_inline) may only say "certainly rejected" for candidates the exact
+    P3P + reprojection check (cnn_softam.h:1041-1059) rejects; it should also flag only a few percent."""
+    import ctypes as C
+    E = engine_mod
+    coords, pix, _, _ = E.synth_frames(4)
+    tot = np.zeros(6, np.int64)
+    for i in range(4):
+        out = (C.c_longlong * 6)()
+        host_shim.shim_filter_stats(coords[i].ctypes.data_as(C.c_void_p), pix[i].ctypes.data_as(C.c_void_p), C.c_uint32(1305 + i),
+                                    C.c_uint32(6400 if i == 0 else 0), C.c_int(100000), C.c_double(525), C.c_double(320),
+                                    C.c_double(240), C.c_int(10), out)
+        tot += np.array(list(out))
+    n, acc, flagged, _, missed, _ = [int(v) for v in tot]
+    assert n == 400000 and acc > 3000
+    assert missed == 0
+    assert flagged < 0.03 * n
