@@ -127,6 +127,93 @@ struct BwParams {
     BackwardScratch s;
 };
 
+// ------------------------------------------------------------------ DSAC / RANSAC variant (train_ransac.cpp:304-381)
+// dRefine of hypothesis h (cnn.h:866-990) is a list of refine() evaluations (cnn.h:787-852); each is one k_refine job.
+// The jobs that perturb a minimal-set point start from the P3P pose of the PERTURBED set: this kernel computes it.
+struct DsacBwParams {
+    const int16_t* coords;
+    const int32_t* pix;
+    int pix_stride;
+    double f, cx, cy;
+    int H;
+    const int32_t* img_idx;     // [n][H][4]
+    const double* ref_pose;     // [n*H][6] refined cv pose of every hypothesis (forward_dsac)
+    const double* sf;           // [n*H]
+    const double* gt_jp;        // [n][12]
+    // jobs
+    int n_jobs;
+    const int32_t* job_frame;   // [n_jobs]
+    const int32_t* job_p3p;     // [n_jobs][3] {global hypothesis index or -1, point*3+channel, delta}
+    double* job_init;           // [n_jobs][6]
+    const double* job_jp6;      // [n_jobs][6] results of k_refine
+    // central-difference pairs (jobs 2p, 2p+1 = forward, backward step), sorted by frame, hypothesis
+    int n_frames;
+    const int32_t* frame_pair_begin;   // [n+1]
+    const int32_t* pair_hyp;    // [n_pairs] global hypothesis index
+    const int32_t* pair_col;    // [n_pairs] cell*3+channel
+    const int32_t* pair_scale;  // [n_pairs] 1 or skip
+    double* path1;              // [n][N*3]
+};
+
+__global__ void k_dsac_job_p3p(DsacBwParams p) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.n_jobs) return;
+    const int hyp = p.job_p3p[j * 3];
+    if (hyp < 0) return;
+    const int frame = p.job_frame[j];
+    const int16_t* coords = p.coords + (size_t)frame * DSAC_N_CONST * 3;
+    const int32_t* pix = p.pix + (size_t)frame * p.pix_stride;
+    const int32_t* idx = p.img_idx + (size_t)hyp * 4;
+    float obj[12], img[8];
+    for (int q = 0; q < 4; q++) {
+        const int c = idx[q];
+        img[q * 2] = (float)pix[c * 2];
+        img[q * 2 + 1] = (float)pix[c * 2 + 1];
+        for (int k = 0; k < 3; k++) obj[q * 3 + k] = (float)coords[c * 3 + k];
+    }
+    obj[p.job_p3p[j * 3 + 1]] += (float)p.job_p3p[j * 3 + 2];   // objPts[pt] +/- eps (integers in float: exact)
+    double pose[6], R[9], t[3], e2;
+    P3PProblem pr;
+    make_problem(obj, img, p.f, p.cx, p.cy, pr);
+    if (p3p_best(pr, p.f, p.cx, p.cy, R, t, &e2) > 0) {
+        rodrigues_m2v(R, pose);
+        pose[3] = t[0]; pose[4] = t[1]; pose[5] = t[2];
+    } else {
+        for (int k = 0; k < 6; k++) pose[k] = 0;   // safeSolvePnP leaves a zero pose (cnn.h:66-71)
+    }
+    for (int k = 0; k < 6; k++) p.job_init[(size_t)j * 6 + k] = pose[k];
+}
+
+// path I: dLoss_dObj(idx, c) += sf_h * (dLossMax(refined_h, gt) . dRefine_h)(idx*3+c), hypotheses and columns in the
+// reference's order (one thread per frame: the sums are reproducible)
+__global__ void k_dsac_combine(DsacBwParams p) {
+    const int frame = blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= p.n_frames) return;
+    double* row = p.path1 + (size_t)frame * DSAC_N_CONST * 3;
+    const double* g = p.gt_jp + (size_t)frame * 12;
+    double gt6[6];
+    rodrigues_m2v(g, gt6);
+    gt6[3] = g[9]; gt6[4] = g[10]; gt6[5] = g[11];
+    int cur = -1;
+    double dl[6] = {0, 0, 0, 0, 0, 0}, sf = 0;
+    for (int q = p.frame_pair_begin[frame]; q < p.frame_pair_begin[frame + 1]; q++) {
+        const int hyp = p.pair_hyp[q];
+        if (hyp != cur) {
+            cur = hyp;
+            double ref6[6];
+            jp6_from_cv_dev(p.ref_pose + (size_t)hyp * 6, ref6);
+            dloss_max_dev(ref6, gt6, dl);
+            sf = p.sf[hyp];
+        }
+        const double* fS = p.job_jp6 + (size_t)(2 * q) * 6;
+        const double* bS = fS + 6;
+        const double scale = (double)p.pair_scale[q];
+        double acc = 0;
+        for (int k = 0; k < 6; k++) acc += dl[k] * ((fS[k] - bS[k]) / 4.0 * scale);   // / (2 * eps), eps = 2; * skip
+        row[p.pair_col[q]] += sf * acc;
+    }
+}
+
 // ---- per frame: dLossMax and the refine job list (one warp, lane 0 does the serial scan)
 __global__ void k_bw_prep(BwParams p, int n) {
     const int frame = blockIdx.x * blockDim.x + threadIdx.x;
@@ -566,3 +653,5 @@ __global__ void k_kabsch(int n, int m, const double* __restrict__ a, const doubl
 int backward_run(dsac_engine* e, int32_t n, const int16_t* coords, const int32_t* pix, int32_t pix_shared,
                  const double* gt_jp, dsac_backward_out* out);
 int kabsch_run(dsac_engine* e, int32_t n, int32_t m, const double* a, const double* b, double* R, double* t);
+struct dsac_backward_dsac_out;
+int backward_dsac_run(dsac_engine* e, int32_t n, dsac_backward_dsac_out* out);

@@ -41,6 +41,7 @@ struct dsac_engine {
     int cur_pix_shared = 0;
     const double* cur_gt = nullptr;
     int cur_n = 0;
+    int dsac_n = 0;                 // frames of the last dsac_forward_dsac (0: none), for dsac_backward_dsac
     long long cur_frame0 = 0;
     // state
     uint16_t* d_perm = nullptr;
@@ -318,17 +319,8 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
         kp.alpha = c.alpha;
         kp.external_scores = 0;
         dim3 grid(kp.tiles_per_frame, n);
-        static const int k2v = getenv("DSAC_K2_VARIANT") ? atoi(getenv("DSAC_K2_VARIANT")) : 0;   // experiment switch
-        const bool dmw = e->d_diffmaps != nullptr;
-#define K2_LAUNCH(KERN) do { if (dmw) KERN<<<grid, K2_THREADS, 0, stream>>>(kp); else KERN<<<grid, K2_THREADS, 0, stream>>>(kp); } while (0)
-        switch (k2v) {
-            case 1: if (dmw) k_score<true, true><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score<false, true><<<grid, K2_THREADS, 0, stream>>>(kp); break;
-            case 2: if (dmw) k_score2<true, 0><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score2<false, 0><<<grid, K2_THREADS, 0, stream>>>(kp); break;
-            case 3: if (dmw) k_score2<true, 1><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score2<false, 1><<<grid, K2_THREADS, 0, stream>>>(kp); break;
-            case 4: if (dmw) k_score2<true, 2><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score2<false, 2><<<grid, K2_THREADS, 0, stream>>>(kp); break;
-            default: if (dmw) k_score<true, false><<<grid, K2_THREADS, 0, stream>>>(kp); else k_score<false, false><<<grid, K2_THREADS, 0, stream>>>(kp); break;
-        }
-#undef K2_LAUNCH
+        if (e->d_diffmaps) k_score<true><<<grid, K2_THREADS, 0, stream>>>(kp);
+        else k_score<false><<<grid, K2_THREADS, 0, stream>>>(kp);
         e->launches++;
         CU(cudaGetLastError());
         if (e->hook) {
@@ -377,6 +369,7 @@ int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
     e->cur_pix_shared = pix_shared;
     e->cur_gt = d_gt_jp;
     e->cur_n = n;
+    e->dsac_n = 0;
     e->cur_frame0 = frame0;
     return forward_range(e, 0, n, frame0, d_coords, d_pix, pix_shared, d_gt_jp, stream_v);
 }
@@ -463,6 +456,7 @@ int dsac_forward(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coord
     e->cur_pix_shared = pix_shared;
     e->cur_gt = gt_jp ? e->d_gt : nullptr;
     e->cur_n = n;
+    e->dsac_n = 0;
     e->cur_frame0 = frame0;
     // Frames are independent, so the batch is cut into up to 4 chunks, each on its own stream:
     // H2D(chunk) -> K1 -> K2 -> K4 -> D2H(chunk).  Copies of later chunks overlap the kernels of earlier
@@ -536,6 +530,7 @@ int dsac_forward_dsac(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* 
     if (gt_jp) CU(cudaMemcpyAsync(e->d_gt, gt_jp, nn * 12 * sizeof(double), cudaMemcpyHostToDevice, stream));
     e->cur_coords = e->d_coords; e->cur_pix = e->d_pix; e->cur_pix_shared = pix_shared; e->cur_gt = gt_jp ? e->d_gt : nullptr;
     e->cur_n = 0;   // the soft-argmax backward does not apply to this pass
+    e->dsac_n = 0;
     e->cur_frame0 = frame0;
     const uint32_t saved = e->stages;
     e->stages = DSAC_STAGE_SAMPLE | DSAC_STAGE_SCORE;
@@ -633,6 +628,7 @@ int dsac_forward_dsac(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* 
                     if (cidx >= 0) out->inlier_maps[(f * H + h) * N + cidx] = 0;
                 }
     }
+    e->dsac_n = n;
     return DSAC_OK;
 }
 
@@ -640,6 +636,11 @@ int dsac_backward(dsac_engine* e, int32_t n, const int16_t* coords, const int32_
                   const double* gt_jp, dsac_backward_out* out) {
     if (!e || !out) return DSAC_ERR_ARG;
     return backward_run(e, n, coords, pix, pix_shared, gt_jp, out);
+}
+
+int dsac_backward_dsac(dsac_engine* e, int32_t n, dsac_backward_dsac_out* out) {
+    if (!e || !out) return DSAC_ERR_ARG;
+    return backward_dsac_run(e, n, out);
 }
 
 int dsac_kabsch(dsac_engine* e, int32_t n, int32_t m, const double* a, const double* b, double* R, double* t) {
@@ -650,3 +651,4 @@ int dsac_kabsch(dsac_engine* e, int32_t n, int32_t m, const double* a, const dou
 }  // extern "C"
 
 #include "backward_host.inc"
+#include "backward_dsac_host.inc"

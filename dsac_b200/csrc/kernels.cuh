@@ -574,7 +574,7 @@ struct ScoreParams {
 };
 
 constexpr int K2_THREADS = 320;  // 10 warps x 5 points per thread = 1600 scene coordinates
-constexpr int K2_PTS = 5;
+constexpr int K2_PTS = 5;   // (the one-reciprocal sigmoid sum in k_score is written out for exactly 5)
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_MAX_TILE = 256;
 
@@ -652,7 +652,7 @@ __device__ void softargmax_tail(const ScoreParams& p, int frame, double* s_red /
     }
 }
 
-template <bool WRITE_DM, bool ONE_RCP = false>
+template <bool WRITE_DM>
 __global__ void __launch_bounds__(K2_THREADS, 3) k_score(ScoreParams p) {
     __shared__ __align__(16) float s_P[K2_MAX_TILE * 12];
     __shared__ float s_part[K2_WARPS][K2_MAX_TILE];
@@ -704,8 +704,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k_score(ScoreParams p) {
                     const float4 r2 = *reinterpret_cast<const float4*>(s_P + h * 12 + 8);
                     // Per point: ONE rsqrt gives the clamped reprojection error,
                     //   e = |pix - proj| = sqrt(A)/|z|,  A = (pu*z - xs)^2 + (pv*z - ys)^2  ->  e = A * rsqrt(A * z^2),
-                    // and the sigmoids of two points share ONE reciprocal:
-                    //   1/(1+t1) + 1/(1+t2) = (2 + t1 + t2) / ((1+t1)(1+t2)),  t = 2^(kbeta*(e - tau)) clamped to 2^60.
+                    // and the thread's five sigmoids share ONE reciprocal (below),  t = 2^(kbeta*(e - tau)) clamped to 2^25.
                     float t[K2_PTS];
 #pragma unroll
                     for (int j = 0; j < K2_PTS; j++) {
@@ -719,17 +718,15 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k_score(ScoreParams p) {
                         float e = A * fast_rsqrt(A * (zs * zs));
                         e = (A > 0.f) ? fminf(e, DSAC_MAXINPUT_F) : 0.f;  // min(norm, CNN_OBJ_MAXINPUT), cnn_softam.h:357
                         if (WRITE_DM) __stcs(dm + (size_t)h * DSAC_N_CONST + tid + j * K2_THREADS, e);
-                        t[j] = fminf(fast_ex2(fmaf(p.kbeta, e, -tau_k)), ONE_RCP ? 33554432.f : 1.152921504606847e18f);
+                        t[j] = fminf(fast_ex2(fmaf(p.kbeta, e, -tau_k)), 33554432.f);
                     }
-                    if (ONE_RCP) {
-                        // all five sigmoids over ONE reciprocal: sum_j 1/u_j = N/D, u = 1+t <= 2^25+1 so D < 2^126
+                    {
+                        // all five sigmoids over ONE reciprocal: sum_j 1/u_j = N/D with u_j = 1 + t_j <= 2^25 + 1, so D < 2^126
+                        // (a sigmoid below 2^-25 is rounded up to 2^-25: <= 5e-6 absolute on a score, far inside tolerance)
                         float u0 = 1.f + t[0], u1 = 1.f + t[1], u2 = 1.f + t[2], u3 = 1.f + t[3], u4 = 1.f + t[4];
                         float p01 = u0 * u1, p23 = u2 * u3, q = p23 * u4;
                         float N = fmaf(u0 + u1, q, p01 * fmaf(u2 + u3, u4, p23));
                         a = N * fast_rcp(p01 * q);
-                    } else {
-                        float d01 = (1.f + t[0]) * (1.f + t[1]), d23 = (1.f + t[2]) * (1.f + t[3]);
-                        a = (2.f + t[0] + t[1]) * fast_rcp(d01) + (2.f + t[2] + t[3]) * fast_rcp(d23) + fast_rcp(1.f + t[4]);
                     }
                 }
                 acc[u] = a;
@@ -772,175 +769,6 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k_score(ScoreParams p) {
         unsigned int prev = atomicAdd(p.frame_counter + frame, 1u);
         s_last = (prev == (unsigned int)p.tiles_per_frame - 1u);
         if (s_last) p.frame_counter[frame] = 0u;  // self-reset for the next launch
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        softargmax_tail(p, frame, s_red);
-    }
-}
-
-// ------------------------------------------------------------------ K2, packed variant
-// Same computation as k_score with Blackwell's packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2): one
-// instruction works on TWO hypotheses.  The tile's projection rows are staged interleaved by hypothesis
-// pair, (row_h, row_h+1) as float2, so every operand arrives as a natural 64-bit pair; the thread's scene
-// coordinates are held "splatted" (X, X).  Roughly 19 issue slots per (hypothesis, point) instead of 33.
-__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
-
-template <bool WRITE_DM, int MODE>
-__global__ void __launch_bounds__(K2_THREADS, 2) k_score2(ScoreParams p) {
-    __shared__ __align__(16) float2 s_P2[(K2_MAX_TILE / 2) * 12];
-    __shared__ float s_part[K2_WARPS][K2_MAX_TILE];
-    __shared__ double s_red[8 * K2_WARPS];
-    __shared__ unsigned int s_last;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int frame = blockIdx.y, tile_idx = blockIdx.x;
-    const int hbeg = tile_idx * p.tile;
-    const int nh = min(p.tile, p.H - hbeg);
-
-    if (!p.external_scores) {
-        float2 X[K2_PTS], Y[K2_PTS], Z[K2_PTS], pu[K2_PTS], pv[K2_PTS];
-        {
-            const int16_t* c = p.coords + (size_t)frame * DSAC_N_CONST * 3;
-            const int2* px = reinterpret_cast<const int2*>(p.pix + (size_t)frame * p.pix_stride);
-#pragma unroll
-            for (int j = 0; j < K2_PTS; j++) {
-                int pt = tid + j * K2_THREADS;
-                X[j] = splat2((float)__ldg(c + pt * 3));
-                Y[j] = splat2((float)__ldg(c + pt * 3 + 1));
-                Z[j] = splat2((float)__ldg(c + pt * 3 + 2));
-                int2 q = __ldg(px + pt);
-                pu[j] = splat2((float)q.x - p.cxf);
-                pv[j] = splat2((float)q.y - p.cyf);
-            }
-        }
-        {   // stage the tile's rows interleaved by hypothesis pair; an odd tail pairs the last hypothesis with itself
-            const float* src = p.hyp_P + ((size_t)frame * p.H + hbeg) * 12;
-            float* dst = reinterpret_cast<float*>(s_P2);
-            const int nh2 = (nh + 1) & ~1;
-            for (int i = tid; i < nh2 * 12; i += K2_THREADS) {
-                int h = i / 12, c = i - h * 12;
-                int hs = min(h, nh - 1);
-                dst[((h >> 1) * 12 + c) * 2 + (h & 1)] = __ldg(src + hs * 12 + c);
-            }
-        }
-        __syncthreads();
-
-        float* dm = WRITE_DM ? p.diffmaps + ((size_t)frame * p.H + hbeg) * DSAC_N_CONST : nullptr;
-        const float2 kb2 = splat2(p.kbeta), ntk2 = splat2(-p.thr * p.kbeta), one2 = splat2(1.f), two2 = splat2(2.f);
-
-        for (int hb = 0; hb < nh; hb += 8) {
-            float acc[8];
-#pragma unroll
-            for (int u2 = 0; u2 < 4; u2++) {
-                const int h = hb + 2 * u2;   // hypotheses h, h+1
-                float2 a = make_float2(0.f, 0.f);
-                if (h < nh) {
-                    const float2* P = s_P2 + (h >> 1) * 12;
-                    const float2 r0x = P[0], r0y = P[1], r0z = P[2], r0w = P[3];
-                    const float2 r1x = P[4], r1y = P[5], r1z = P[6], r1w = P[7];
-                    const float2 r2x = P[8], r2y = P[9], r2z = P[10], r2w = P[11];
-                    float2 t[K2_PTS];
-#pragma unroll
-                    for (int j = 0; j < K2_PTS; j++) {
-                        float2 xs = __ffma2_rn(r0x, X[j], __ffma2_rn(r0y, Y[j], __ffma2_rn(r0z, Z[j], r0w)));
-                        float2 ys = __ffma2_rn(r1x, X[j], __ffma2_rn(r1y, Y[j], __ffma2_rn(r1z, Z[j], r1w)));
-                        float2 zs = __ffma2_rn(r2x, X[j], __ffma2_rn(r2y, Y[j], __ffma2_rn(r2z, Z[j], r2w)));
-                        zs.x = (zs.x != 0.f) ? zs.x : 1.f;   // z ? 1/z : 1 (cv::projectPoints)
-                        zs.y = (zs.y != 0.f) ? zs.y : 1.f;
-                        float2 du = __ffma2_rn(pu[j], zs, make_float2(-xs.x, -xs.y));
-                        float2 dv = __ffma2_rn(pv[j], zs, make_float2(-ys.x, -ys.y));
-                        float2 A = __ffma2_rn(du, du, __fmul2_rn(dv, dv));
-                        float2 Az = __fmul2_rn(A, __fmul2_rn(zs, zs));
-                        float2 rs = make_float2(fast_rsqrt(fmaxf(Az.x, 1e-30f)), fast_rsqrt(fmaxf(Az.y, 1e-30f)));
-                        float2 e = __fmul2_rn(A, rs);   // |pix - proj| = A * rsqrt(A z^2); A == 0 -> 0
-                        e.x = fminf(e.x, DSAC_MAXINPUT_F);   // min(norm, CNN_OBJ_MAXINPUT), cnn_softam.h:357
-                        e.y = fminf(e.y, DSAC_MAXINPUT_F);
-                        if (WRITE_DM) {
-                            float* row = dm + (size_t)h * DSAC_N_CONST + tid + j * K2_THREADS;
-                            __stcs(row, e.x);
-                            if (h + 1 < nh) __stcs(row + DSAC_N_CONST, e.y);
-                        }
-                        float2 arg = __ffma2_rn(kb2, e, ntk2);
-                        if (MODE == 2) {
-                            // 2^x on the FMA pipe: x = n + f, f in [-.5,.5], degree-5 polynomial, exponent spliced in
-                            arg.x = fminf(arg.x, 25.f);
-                            arg.y = fminf(arg.y, 25.f);
-                            const float2 mg = splat2(12582912.f), nmg = splat2(-12582912.f);
-                            float2 fi = __fadd2_rn(arg, mg);
-                            float2 n = __fadd2_rn(fi, nmg);
-                            float2 f = __fadd2_rn(arg, make_float2(-n.x, -n.y));
-                            float2 q = __ffma2_rn(splat2(0.0013400432653725147f), f, splat2(0.009676037356257439f));
-                            q = __ffma2_rn(q, f, splat2(0.05550327152013779f));
-                            q = __ffma2_rn(q, f, splat2(0.2402210682630539f));
-                            q = __ffma2_rn(q, f, splat2(0.6931471824645996f));
-                            q = __ffma2_rn(q, f, splat2(1.0000001192092896f));
-                            t[j] = make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(fi.x) << 23)),
-                                               __int_as_float(__float_as_int(q.y) + (__float_as_int(fi.y) << 23)));
-                        } else {
-                            const float cap = MODE ? 33554432.f : 1.152921504606847e18f;
-                            t[j] = make_float2(fminf(fast_ex2(arg.x), cap), fminf(fast_ex2(arg.y), cap));
-                        }
-                    }
-                    if (MODE) {
-                        float2 u0 = __fadd2_rn(one2, t[0]), u1 = __fadd2_rn(one2, t[1]), u2v = __fadd2_rn(one2, t[2]),
-                               u3 = __fadd2_rn(one2, t[3]), u4 = __fadd2_rn(one2, t[4]);
-                        float2 p01 = __fmul2_rn(u0, u1), p23 = __fmul2_rn(u2v, u3), q = __fmul2_rn(p23, u4);
-                        float2 N = __ffma2_rn(__fadd2_rn(u0, u1), q, __fmul2_rn(p01, __ffma2_rn(__fadd2_rn(u2v, u3), u4, p23)));
-                        float2 D = __fmul2_rn(p01, q);
-                        a = __fmul2_rn(N, make_float2(fast_rcp(D.x), fast_rcp(D.y)));
-                    } else {
-                    // sum_j 1/(1+t_j) with one reciprocal per two points
-                    float2 u0 = __fadd2_rn(one2, t[0]), u1 = __fadd2_rn(one2, t[1]), u2v = __fadd2_rn(one2, t[2]),
-                           u3 = __fadd2_rn(one2, t[3]), u4 = __fadd2_rn(one2, t[4]);
-                    float2 d01 = __fmul2_rn(u0, u1), d23 = __fmul2_rn(u2v, u3);
-                    float2 n01 = __fadd2_rn(u0, u1), n23 = __fadd2_rn(u2v, u3);   // (1+t0)+(1+t1) = 2+t0+t1
-                    float2 r01 = make_float2(fast_rcp(d01.x), fast_rcp(d01.y)), r23 = make_float2(fast_rcp(d23.x), fast_rcp(d23.y));
-                    float2 r4 = make_float2(fast_rcp(u4.x), fast_rcp(u4.y));
-                    a = __ffma2_rn(n01, r01, __ffma2_rn(n23, r23, r4));
-                    }
-                    (void)two2;
-                }
-                acc[2 * u2] = a.x;
-                acc[2 * u2 + 1] = a.y;
-            }
-            // transposed warp reduction: 8 partials -> lane (4*b4+2*b3+b2) group holds hypothesis sum
-#pragma unroll
-            for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i < half) {
-                        float send = up ? acc[i] : acc[i + half];
-                        float keep = up ? acc[i + half] : acc[i];
-                        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
-                }
-            }
-            float v = acc[0];
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((lane & 3) == 0) {
-                int u = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                if (hb + u < nh) s_part[warp][hb + u] = v;
-            }
-        }
-        __syncthreads();
-        for (int h = tid; h < nh; h += K2_THREADS) {
-            float ssum = 0.f;
-#pragma unroll
-            for (int w = 0; w < K2_WARPS; w++) ssum += s_part[w][h];
-            p.scores[(size_t)frame * p.H + hbeg + h] = p.alpha * (double)ssum;
-        }
-    }
-
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int prev = atomicAdd(p.frame_counter + frame, 1u);
-        s_last = (prev == (unsigned int)p.tiles_per_frame - 1u);
-        if (s_last) p.frame_counter[frame] = 0u;
     }
     __syncthreads();
     if (s_last) {

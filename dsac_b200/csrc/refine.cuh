@@ -36,6 +36,7 @@ struct RefineParams {
     const double* job_init;     // [n_jobs][6] cv pose
     const int32_t* job_pert;    // [n_jobs][2] {cell*3+chan or -1, delta} or null
     const int32_t* max_steps;   // [n_frames] replay limit (n_perm_steps of the forward) or null
+    const int32_t* job_max_steps;   // [n_jobs] replay limit per job (DSAC variant: per hypothesis) or null
     // outputs
     double* out_pose;           // [n_jobs][6] refined cv pose
     double* out_jp6;            // [n_jobs][6] Hypothesis(cv2our(pose)).getRodVecAndTrans() or null
@@ -240,7 +241,8 @@ __global__ void __launch_bounds__(K4_THREADS) k_refine(RefineParams p) {
         pert_idx = p.job_pert[job * 2];
         pert_delta = p.job_pert[job * 2 + 1];
     }
-    const int step_limit = p.max_steps ? min(p.ref_steps, p.max_steps[frame]) : p.ref_steps;
+    const int step_limit = p.job_max_steps ? min(p.ref_steps, p.job_max_steps[job])
+                                           : (p.max_steps ? min(p.ref_steps, p.max_steps[frame]) : p.ref_steps);
 
     auto coord = [&](int c, int k) -> double {
         int v = coords[c * 3 + k];

@@ -20,7 +20,8 @@ ST_SAMPLER_EXHAUSTED, ST_REFINE_ABORTED = 1, 2
 EXPORTS = [
     "dsac_default_config", "dsac_engine_create", "dsac_engine_destroy", "dsac_last_error", "dsac_engine_config",
     "dsac_forward", "dsac_forward_device", "dsac_fetch", "dsac_device_view_get", "dsac_set_stages",
-    "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_forward_dsac", "dsac_kabsch", "dsac_stochastic_subsample",
+    "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_kabsch",
+    "dsac_stochastic_subsample",
     "dsac_synth_frames", "dsac_version",
 ]
 
@@ -103,6 +104,7 @@ def load(build_if_missing=True):
                                   C.POINTER(BackwardOut)]
     lib.dsac_forward_dsac.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                       C.POINTER(DsacOut)]
+    lib.dsac_backward_dsac.argtypes = [C.c_void_p, C.c_int32, C.POINTER(BackwardDsacOut)]
     lib.dsac_kabsch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dsac_stochastic_subsample.argtypes = [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]
     lib.dsac_synth_frames.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_int64, C.c_int32, C.c_double, C.c_double,
@@ -184,6 +186,24 @@ class DsacResult:
         self.rot_err = np.zeros(n); self.t_err = np.zeros(n); self.correct = np.zeros(n, np.int32); self.status = np.zeros(n, np.uint32)
         self.raw = DsacOut()
         for k in _DSAC_FIELDS:
+            setattr(self.raw, k, _p(getattr(self, k)))
+
+
+_BWD_FIELDS = ("dloss_dobj", "path1", "path2", "score_grads", "n_selected", "n_refine_jobs")
+
+
+class BackwardDsacOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in _BWD_FIELDS]
+
+
+class BackwardDsacResult:
+    """dsac_backward_dsac outputs (train_ransac.cpp:304-381)."""
+
+    def __init__(self, n, H):
+        self.dloss_dobj = np.zeros((n, N, 3)); self.path1 = np.zeros((n, N, 3)); self.path2 = np.zeros((n, N, 3))
+        self.score_grads = np.zeros((n, H)); self.n_selected = np.zeros(n, np.int32); self.n_refine_jobs = np.zeros(n, np.int32)
+        self.raw = BackwardDsacOut()
+        for k in _BWD_FIELDS:
             setattr(self.raw, k, _p(getattr(self, k)))
 
 
@@ -298,6 +318,12 @@ class Engine:
         gt = np.ascontiguousarray(gt_jp, np.float64).reshape(n, 12)
         res = BackwardResult(n, self.cfg.n_hyps, full)
         self._check(self.lib.dsac_backward(self.h, n, _p(coords), _p(pix), shared, _p(gt), C.byref(res.raw)))
+        return res
+
+    def backward_dsac(self, n):
+        """dsac_backward_dsac: gradients of the expected loss of the DSAC variant; follows forward_dsac over n frames."""
+        res = BackwardDsacResult(n, self.cfg.n_hyps)
+        self._check(self.lib.dsac_backward_dsac(self.h, n, C.byref(res.raw)))
         return res
 
     def kabsch(self, a, b):

@@ -189,6 +189,24 @@ typedef struct dsac_dsac_out {
 int dsac_forward_dsac(dsac_engine* e, int32_t n_frames, int64_t frame0, const int16_t* coords, const int32_t* pix,
                       int32_t pix_shared, const double* gt_jp, int32_t random_draw, dsac_dsac_out* out);
 
+/* Backward of the DSAC / RANSAC variant (replaces the gradient block of train_ransac.cpp:304-381; must follow a
+ * dsac_forward_dsac over the same n_frames with ground truth):
+ *   path I  : sum over the hypotheses with sf_h > 1e-4 of sf_h * dLossMax(refined_h, gt) (maxloss.h:87) * dRefine_h
+ *             (cnn.h:866-990: central differences with eps = 2 through refine(), cnn.h:787-852 -- 18 evaluations on the
+ *             perturbed minimal set plus 6 per sub-sampled inlier pixel, all of them jobs of the refinement kernel);
+ *   path II : dSMScore (cnn.h:726-767) with scoreOutputGradients_i = sf_i * (loss_i - sum_j sf_j loss_j)
+ *             (cnn.h:733-741) and the closed-form score backward at the score seam, rows in row-major order.
+ * dloss_dobj = path I + path II is what train_ransac.cpp:399 hands to backward() of the coordinate CNN. */
+typedef struct dsac_backward_dsac_out {
+    double* dloss_dobj;       /* [n][N][3]  dLoss_dObj               train_ransac.cpp:353-377 */
+    double* path1;            /* [n][N][3]  nullable */
+    double* path2;            /* [n][N][3]  nullable */
+    double* score_grads;      /* [n][H]     scoreOutputGradients, nullable  cnn.h:733-741 */
+    int32_t* n_selected;      /* [n]        hypotheses with sf > 1e-4, nullable */
+    int32_t* n_refine_jobs;   /* [n]        refine() evaluations of path I, nullable */
+} dsac_backward_dsac_out;
+int dsac_backward_dsac(dsac_engine* e, int32_t n_frames, dsac_backward_dsac_out* out);
+
 /* Batched Kabsch (Hypothesis::calcRigidBodyTransform, Hypothesis.cpp:145-200):
  * for each of n problems with m correspondences, b ~ R a + t.  a,b: [n][m][3] doubles. */
 int dsac_kabsch(dsac_engine* e, int32_t n, int32_t m, const double* a, const double* b, double* R /* [n][9] */,

@@ -55,6 +55,13 @@ class DsacOut(C.Structure):
     ]
 
 
+class BackwardDsacOut(C.Structure):
+    _fields_ = [
+        ("dloss_dobj", C.c_void_p), ("path1", C.c_void_p), ("path2", C.c_void_p), ("score_grads", C.c_void_p),
+        ("n_selected", C.c_int32), ("n_refine_jobs", C.c_int32),
+    ]
+
+
 class BackwardOut(C.Structure):
     _fields_ = [
         ("dloss_dobj", C.c_void_p), ("dloss_dref", C.c_double * 6), ("dref_dobj", C.c_void_p),
@@ -376,6 +383,33 @@ def backward(cfg, coords, pix, gt_R, gt_t, fwd):
     gt = np.ascontiguousarray(gt_t, np.float64).reshape(3)
     out = Backward(cfg)
     lib().orc_backward(C.byref(cfg), _p(coords), _p(pix), _p(gR), _p(gt), C.byref(fwd.raw), C.byref(out.raw))
+    return out
+
+
+class BackwardDsac:
+    def __init__(self, cfg):
+        self.dloss_dobj = np.zeros((N, 3)); self.path1 = np.zeros((N, 3)); self.path2 = np.zeros((N, 3))
+        self.score_grads = np.zeros(cfg.n_hyps)
+        self.raw = BackwardDsacOut()
+        for k in ("dloss_dobj", "path1", "path2", "score_grads"):
+            setattr(self.raw, k, _p(getattr(self, k)))
+
+    def __getattr__(self, k):
+        raw = self.__dict__.get("raw")
+        if raw is not None and k in ("n_selected", "n_refine_jobs"):
+            return getattr(raw, k)
+        raise AttributeError(k)
+
+
+def backward_dsac(cfg, coords, pix, gt_R, gt_t, fwd):
+    """Backward of the DSAC / RANSAC variant (train_ransac.cpp:304-381) from a forward_dsac result."""
+    coords = np.ascontiguousarray(coords, np.int16).reshape(N, 3)
+    pix = np.ascontiguousarray(pix, np.int32).reshape(N, 2)
+    gR = np.ascontiguousarray(gt_R, np.float64).reshape(9)
+    gt = np.ascontiguousarray(gt_t, np.float64).reshape(3)
+    out = BackwardDsac(cfg)
+    lib().orc_backward_dsac.restype = C.c_int
+    lib().orc_backward_dsac(C.byref(cfg), _p(coords), _p(pix), _p(gR), _p(gt), C.byref(fwd.raw), C.byref(out.raw))
     return out
 
 
