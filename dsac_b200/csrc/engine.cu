@@ -3,6 +3,8 @@
 // CUDA device and fails loudly otherwise.
 #include <cuda_runtime.h>
 
+#include <chrono>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -41,6 +43,7 @@ struct dsac_engine {
     int cur_pix_shared = 0;
     const double* cur_gt = nullptr;
     int cur_n = 0;
+    int k1_slots = 296;             // resident k_sample CTAs on this GPU (SMs x CTAs/SM), set at creation
     int dsac_n = 0;                 // frames of the last dsac_forward_dsac (0: none), for dsac_backward_dsac
     long long cur_frame0 = 0;
     // state
@@ -72,7 +75,9 @@ struct dsac_engine {
     double* d_t_err = nullptr;
     int32_t* d_correct = nullptr;
     unsigned int* d_frame_counter = nullptr;
-    std::vector<long long> h_stream_ncand;
+    long long* h_stream_ncand = nullptr;   // [max_frames][n_streams], pinned (so that a submitted pass stays asynchronous)
+    dsac_forward_out* pending_out = nullptr;   // results of a submitted, not yet awaited pass
+    int pending_n = 0, pending_chunks = 0;
     BackwardScratch bw;
     cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // chunked H2D / compute / D2H pipeline of dsac_forward
 };
@@ -135,7 +140,7 @@ void dsac_engine_destroy(dsac_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     for (cudaStream_t st : e->pipe)
-        if (st) cudaStreamDestroy(st);
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     if (e->d_phase) {
         unsigned long long h[16];
         if (cudaMemcpy(h, e->d_phase, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -149,6 +154,7 @@ void dsac_engine_destroy(dsac_engine* e) {
                     e->d_t_err, e->d_correct, e->d_frame_counter};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (e->h_stream_ncand) cudaFreeHost(e->h_stream_ncand);
     backward_scratch_free(&e->bw);
     delete e;
 }
@@ -245,7 +251,13 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         CUC(cudaMemcpy(e->d_perm, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
     CUC(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
-    e->h_stream_ncand.resize(n * cfg->n_streams);
+    {
+        int per_sm = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample, K1_THREADS, sizeof(K1Smem));
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        if (per_sm > 0 && sms > 0) e->k1_slots = per_sm * sms;
+    }
+    CUC(cudaMallocHost(&e->h_stream_ncand, n * cfg->n_streams * sizeof(long long)));
     for (int i = 0; i < 4; i++) CUC(cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking));
 #undef CUC
     *out = e;
@@ -403,7 +415,7 @@ static int fetch_range(dsac_engine* e, int32_t off, int32_t n, dsac_forward_out*
     D2H(o->correct, e->d_correct, 1);
     D2H(o->status, e->d_status, 1);
     if (o->n_candidates) {
-        long long* hdst = e->h_stream_ncand.data();
+        long long* hdst = e->h_stream_ncand;
         D2H(hdst, e->d_stream_ncand, T);
     }
 #undef D2H
@@ -444,9 +456,10 @@ int dsac_device_view_get(dsac_engine* e, dsac_device_view* v) {
     return DSAC_OK;
 }
 
-int dsac_forward(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
-                 int32_t pix_shared, const double* gt_jp, dsac_forward_out* out) {
+int dsac_forward_submit(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
+                        int32_t pix_shared, const double* gt_jp, dsac_forward_out* out) {
     if (!e) return DSAC_ERR_ARG;
+    if (e->pending_chunks) return fail(e, DSAC_ERR_ARG, "dsac_forward_submit: the previous submitted pass has not been awaited");
     if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
     if (!coords || !pix) return fail(e, DSAC_ERR_ARG, "null input");
     CU(cudaSetDevice(e->cfg.device));
@@ -461,32 +474,77 @@ int dsac_forward(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coord
     // Frames are independent, so the batch is cut into up to 4 chunks, each on its own stream:
     // H2D(chunk) -> K1 -> K2 -> K4 -> D2H(chunk).  Copies of later chunks overlap the kernels of earlier
     // ones and the tail of one chunk's kernels is filled by the next chunk's CTAs.
+    static const bool trace = getenv("DSAC_TRACE") != nullptr;
+    cudaEvent_t tev[4];
+    const auto t_host0 = std::chrono::steady_clock::now();
+    if (trace) for (int k = 0; k < 4; k++) cudaEventCreate(&tev[k]);
     int chunks = 1;   // measured on B200 (tools/e2e_probe.py): 1 chunk 6.03 ms, 2: 6.21, 4: 6.87 -- the sampler kernel wants the whole batch
     if (const char* ev = getenv("DSAC_PIPE_CHUNKS")) chunks = std::max(1, std::min(4, atoi(ev)));
     if (pix_shared) CU(cudaMemcpyAsync(e->d_pix, pix, N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, e->pipe[0]));
     if (pix_shared && chunks > 1) {   // every chunk reads the shared grid: make it visible to all streams first
         CU(cudaStreamSynchronize(e->pipe[0]));
     }
+    // chunk boundaries at whole waves of the sampler (one CTA per frame and stream, e->k1_slots CTAs resident per GPU),
+    // so that a later chunk's CTAs fill the slots an earlier chunk frees instead of adding a partial wave
+    int bound[5] = {0, n, n, n, n};
+    if (chunks > 1) {
+        const int per_wave = std::max(1, e->k1_slots / std::max(1, e->cfg.n_streams));
+        const int waves = (n + per_wave - 1) / per_wave;
+        for (int c = 1; c < chunks; c++) bound[c] = std::min(n, std::max(1, (int)((long long)waves * c / chunks)) * per_wave);
+        bound[chunks] = n;
+    }
     for (int c = 0; c < chunks; c++) {
-        const int lo = (int)((long long)n * c / chunks), hi = (int)((long long)n * (c + 1) / chunks), m = hi - lo;
+        const int lo = bound[c], hi = bound[c + 1], m = hi - lo;
         if (m <= 0) continue;
         cudaStream_t st = e->pipe[c];
         const size_t f = (size_t)lo;
+        if (trace) cudaEventRecord(tev[0], st);
         CU(cudaMemcpyAsync(e->d_coords + f * N * 3, coords + f * N * 3, (size_t)m * N * 3 * sizeof(int16_t), cudaMemcpyHostToDevice, st));
         if (!pix_shared)
             CU(cudaMemcpyAsync(e->d_pix + f * N * 2, pix + f * N * 2, (size_t)m * N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         if (gt_jp) CU(cudaMemcpyAsync(e->d_gt + f * 12, gt_jp + f * 12, (size_t)m * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (trace) cudaEventRecord(tev[1], st);
         int rc = forward_range(e, lo, m, frame0 + lo, e->d_coords + f * N * 3, pix_shared ? e->d_pix : e->d_pix + f * N * 2,
                                pix_shared, gt_jp ? e->d_gt + f * 12 : nullptr, st);
         if (rc != DSAC_OK) return rc;
+        if (trace) cudaEventRecord(tev[2], st);
         if (out) {
             rc = fetch_range(e, lo, m, out, st);
             if (rc != DSAC_OK) return rc;
         }
+        if (trace) cudaEventRecord(tev[3], st);
     }
-    for (int c = 0; c < chunks; c++) CU(cudaStreamSynchronize(e->pipe[c]));
-    if (out) sum_candidates(e, n, out);
+    e->pending_out = out;
+    e->pending_n = n;
+    e->pending_chunks = chunks;
+    if (trace) {   // DSAC_TRACE=1: where one pass spends its time (last chunk's stream); forces the wait
+        for (int c = 0; c < chunks; c++) CU(cudaStreamSynchronize(e->pipe[c]));
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]); cudaEventElapsedTime(&d, tev[2], tev[3]);
+        const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+        fprintf(stderr, "[dsac trace] H2D %.3f ms  kernels %.3f ms  D2H %.3f ms  | call %.3f ms (host wall)\n", a, b, d, host_ms);
+        for (int k = 0; k < 4; k++) cudaEventDestroy(tev[k]);
+    }
     return DSAC_OK;
+}
+
+int dsac_forward_wait(dsac_engine* e) {
+    if (!e) return DSAC_ERR_ARG;
+    if (!e->pending_chunks) return DSAC_OK;
+    CU(cudaSetDevice(e->cfg.device));
+    const int chunks = e->pending_chunks;
+    e->pending_chunks = 0;
+    for (int c = 0; c < chunks; c++) CU(cudaStreamSynchronize(e->pipe[c]));
+    if (e->pending_out) sum_candidates(e, e->pending_n, e->pending_out);
+    e->pending_out = nullptr;
+    return DSAC_OK;
+}
+
+int dsac_forward(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
+                 int32_t pix_shared, const double* gt_jp, dsac_forward_out* out) {
+    int rc = dsac_forward_submit(e, n, frame0, coords, pix, pix_shared, gt_jp, out);
+    if (rc != DSAC_OK) return rc;
+    return dsac_forward_wait(e);
 }
 
 int dsac_forward_dsac(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,

@@ -19,7 +19,7 @@ ST_SAMPLER_EXHAUSTED, ST_REFINE_ABORTED = 1, 2
 # every symbol include/dsac_b200.h declares
 EXPORTS = [
     "dsac_default_config", "dsac_engine_create", "dsac_engine_destroy", "dsac_last_error", "dsac_engine_config",
-    "dsac_forward", "dsac_forward_device", "dsac_fetch", "dsac_device_view_get", "dsac_set_stages",
+    "dsac_forward", "dsac_forward_submit", "dsac_forward_wait", "dsac_forward_device", "dsac_fetch", "dsac_device_view_get", "dsac_set_stages",
     "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_kabsch",
     "dsac_stochastic_subsample",
     "dsac_synth_frames", "dsac_version",
@@ -94,6 +94,8 @@ def load(build_if_missing=True):
     lib.dsac_engine_destroy.restype = None
     lib.dsac_forward.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                  C.POINTER(ForwardOut)]
+    lib.dsac_forward_submit.argtypes = lib.dsac_forward.argtypes
+    lib.dsac_forward_wait.argtypes = [C.c_void_p]
     lib.dsac_forward_device.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                         C.c_void_p]
     lib.dsac_fetch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ForwardOut), C.c_void_p]
@@ -269,6 +271,24 @@ class Engine:
         res = out if out is not None else ForwardResult(n, self.cfg.n_hyps, want_diffmaps)
         self._check(self.lib.dsac_forward(self.h, n, frame0, _p(coords), _p(pix), shared, _p(gt), C.byref(res.raw)))
         return res
+
+    def forward_submit(self, coords, pix, gt_jp=None, frame0=0, out=None, want_diffmaps=False):
+        """dsac_forward_submit: enqueue a pass and return; the arrays must stay alive (ideally pinned) until forward_wait()."""
+        coords = np.ascontiguousarray(coords, np.int16).reshape(-1, N, 3)
+        n = coords.shape[0]
+        pix = np.ascontiguousarray(pix, np.int32)
+        shared = 1 if pix.size == N * 2 else 0
+        gt = np.ascontiguousarray(gt_jp, np.float64).reshape(n, 12) if gt_jp is not None else None
+        res = out if out is not None else ForwardResult(n, self.cfg.n_hyps, want_diffmaps)
+        self._pending = (coords, pix, gt, res)
+        self._check(self.lib.dsac_forward_submit(self.h, n, frame0, _p(coords), _p(pix), shared, _p(gt), C.byref(res.raw)))
+        return res
+
+    def forward_wait(self):
+        self._check(self.lib.dsac_forward_wait(self.h))
+        pending = getattr(self, "_pending", None)
+        self._pending = None
+        return pending[3] if pending else None
 
     def forward_device(self, n, d_coords, d_pix, pix_shared=0, d_gt=None, frame0=0, stream=None):
         """dsac_forward_device with raw device pointers (ints)."""

@@ -125,6 +125,15 @@ int dsac_engine_config(const dsac_engine* e, dsac_config* out);
 int dsac_forward(dsac_engine* e, int32_t n_frames, int64_t frame0, const int16_t* coords, const int32_t* pix,
                  int32_t pix_shared, const double* gt_jp, dsac_forward_out* out);
 
+/* The same pass split in two, for drivers that overlap the copies of one batch with the kernels of another
+ * (the frame loop of test_ransac_softam.cpp:107-160 with two engines in flight): dsac_forward_submit enqueues
+ * H2D -> kernels -> D2H on the engine's streams and returns; dsac_forward_wait blocks until the results are in `out`.
+ * coords / pix / gt_jp / out must stay valid (and should be page-locked for the copies to be asynchronous) until the
+ * wait returns; one pass per engine may be pending.  dsac_forward == submit + wait. */
+int dsac_forward_submit(dsac_engine* e, int32_t n_frames, int64_t frame0, const int16_t* coords, const int32_t* pix,
+                        int32_t pix_shared, const double* gt_jp, dsac_forward_out* out);
+int dsac_forward_wait(dsac_engine* e);
+
 /* Same pass with inputs already resident in device memory; results stay on the device
  * (dsac_fetch copies them out).  stream: a cudaStream_t cast to void* (NULL = default). */
 int dsac_forward_device(dsac_engine* e, int32_t n_frames, int64_t frame0, const int16_t* d_coords,

@@ -230,3 +230,19 @@ def test_score_cnn_plugin_behind_the_seam(engine_mod, oracle):
         assert np.abs(O.softmax(res.scores[f]) - res.sf[f]).max() <= 1e-12
         assert np.abs((res.sf[f][:, None] * res.hyp_pose[f]).sum(0) - res.avg_pose[f]).max() <= 1e-9 * 3000
     assert np.isfinite(res.ref_pose).all()
+
+
+def test_submit_wait_equals_blocking_forward(engine_mod):
+    """dsac_forward_submit / dsac_forward_wait (two engines in flight) give what the blocking dsac_forward gives."""
+    E = engine_mod
+    coords, pix, gt_cv, gt_jp = E.synth_frames(6)
+    a, b = E.Engine(max_frames=3, n_hyps=32), E.Engine(max_frames=3, n_hyps=32)
+    ra = a.forward_submit(coords[:3], pix[:3], gt_jp[:3], frame0=0)
+    rb = b.forward_submit(coords[3:], pix[3:], gt_jp[3:], frame0=3)
+    with pytest.raises(RuntimeError):
+        a.forward_submit(coords[:3], pix[:3], gt_jp[:3], frame0=0)      # one pending pass per engine
+    a.forward_wait(); b.forward_wait()
+    a.forward_wait()                                                    # idempotent
+    ref = E.Engine(max_frames=6, n_hyps=32).forward(coords, pix, gt_jp)
+    for k in ("img_idx", "cand_idx", "ref_pose", "avg_pose", "sf", "loss", "n_candidates"):
+        assert np.array_equal(np.concatenate([getattr(ra, k), getattr(rb, k)]), getattr(ref, k)), k

@@ -77,3 +77,14 @@ def test_dsac_variant_driver(apps, tmp_path):
         summ = np.loadtxt(tmp_path / ("ransac_test_loss_obj_model_init.net_rdraw%s.txt" % rdraw))
         assert errs.shape == (12, 11) and summ.shape == (7,)
         assert summ[0] > 0.8 and np.isfinite(errs).all()
+
+
+@pytest.mark.gpu
+def test_dsac_variant_train_driver(apps, tmp_path):
+    """SURVEY.md section 8(f) N1, backward half: train_ransac (core/train_ransac.cpp) in synthetic mode."""
+    out = subprocess.run([os.path.join(apps, "train_ransac"), "-frames", "2", "-rI", "32"], cwd=tmp_path,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Max gradient" in out.stdout and "refinements differentiated" in out.stdout
+    log = np.loadtxt(tmp_path / "ransac_training_loss_train_obj.lua.txt")
+    assert log.shape == (3, 3) and np.isfinite(log).all()
