@@ -61,6 +61,25 @@ def launches(csvf, out):
              "%-60s %8s %14s %8s" % ("kernel", "launches", "total_us", "share")]
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append("%-60s %8d %14.1f %7.1f%%" % (k[:60], n, ns / 1e3, 100 * ns / tot))
+    # the timed step proper = the launches over the full batch (grid has a 1024 in it); bench.py's later sections
+    # (single-frame latency loop, training rounds) launch the same kernels on tiny grids
+    gi = hdr.index("Grid Size") if "Grid Size" in hdr else None
+    if gi is not None:
+        big = OrderedDict()
+        for r in rows[hi + 1:]:
+            if len(r) <= vi or r[mi] != "gpu__time_duration.sum" or "1024" not in r[gi] or "dsac::" not in r[ki]:
+                continue
+            ns = float(r[vi].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[ui], 1)
+            a = big.setdefault(r[ki].split("(")[0], [0, 0.0])
+            a[0] += 1
+            a[1] += ns
+        if big:
+            n_steps = min(a[0] for a in big.values())
+            tot_b = sum(a[1] / a[0] for a in big.values())
+            lines += ["", "# full-batch launches only (1024 frames): average per launch and share of one step",
+                      "%-60s %8s %14s %8s" % ("kernel", "launches", "avg_us", "share")]
+            for k, (n, ns) in sorted(big.items(), key=lambda kv: -kv[1][1] / kv[1][0]):
+                lines.append("%-60s %8d %14.1f %7.1f%%" % (k[:60], n, ns / n / 1e3, 100 * (ns / n) / tot_b))
     open(out, "w").write("\n".join(lines) + "\n")
 
 
