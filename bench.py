@@ -401,6 +401,37 @@ def main():
             train["dsac_variant"]["cpu_ms_per_round_1thread"] = (time.perf_counter() - t0) * 1e3
         eng5.close()
 
+    # ---- upstream step: BGR frame -> normalised CNN patches, a pure streaming kernel
+    upstream = None
+    if rank == 0:
+        nbu = 64
+        rng = np.random.default_rng(7)
+        fr = torch.from_numpy(rng.integers(0, 256, size=(nbu, 480, 640, 3), dtype=np.uint8)).cuda()
+        pxu = torch.from_numpy(pix[:nbu]).cuda()
+        patches = torch.empty((nbu, E.N, 3, 42, 42), dtype=torch.float32, device="cuda")
+        engu = E.Engine(max_frames=1, n_hyps=8, device=local_rank)
+
+        def gather():
+            engu.gather_patches_device(nbu, fr.data_ptr(), 640, 480, pxu.data_ptr(), 0, patches.data_ptr(), stream=stream)
+        for _ in range(3):
+            gather()
+        torch.cuda.synchronize()
+        reps_u = 10
+        tot = 0.0
+        for _ in range(reps_u):
+            flush.zero_()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(); gather(); b_.record(); b_.synchronize()
+            tot += a_.elapsed_time(b_)
+        ms_u = tot / reps_u
+        bytes_u = nbu * (E.N * 3 * 42 * 42 * 4 + 480 * 640 * 3 + E.N * 8)
+        peak_u, _src = peaks()
+        upstream = {"kernel": "k_gather_patches (getCoordImg patch assembly + normalisation, %d frames x 1600 patches of 3x42x42 f32)" % nbu,
+                    "ms_per_launch": ms_u, "algorithmic_bytes_per_launch": bytes_u, "achieved_gbs": bytes_u / (ms_u * 1e-3) / 1e9,
+                    "peak_gbs": peak_u, "frac": bytes_u / (ms_u * 1e-3) / 1e9 / peak_u, "patches_per_s": nbu * E.N / (ms_u * 1e-3)}
+        engu.close()
+        del patches, fr
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
     cpu = None
     if rank == 0 and world == 1:
@@ -437,9 +468,15 @@ def main():
             "gpu_launches": gpu_launches,
             "roofline": roofline,
             "kernels_ms": stage_ms,
+            "sampler": {"kernel": "k_sample (73 % of the step; fp64-latency / barrier-bound, no HBM or tensor roofline applies: "
+                                  "ncu fp64 pipe 32 %, issue 47 %, see profiles/r01_k_sample_full.txt)",
+                        "candidates_per_s": quality["candidates_per_frame"] * nf / (stage_ms["k_sample"] * 1e-3),
+                        "candidates_per_accepted_hypothesis": quality["candidates_per_frame"] / H,
+                        "ms_per_launch": stage_ms["k_sample"]},
             "cpu_baseline": cpu,
             "single_frame": single,
             "train_round": train,
+            "upstream": upstream,
             "quality": quality,
             "clocks": clk,
         }

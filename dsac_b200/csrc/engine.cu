@@ -20,6 +20,7 @@
 #include "backward.cuh"
 #include "kernels.cuh"
 #include "refine.cuh"
+#include "upstream.cuh"
 
 using namespace dsac;
 
@@ -699,6 +700,36 @@ int dsac_backward(dsac_engine* e, int32_t n, const int16_t* coords, const int32_
 int dsac_backward_dsac(dsac_engine* e, int32_t n, dsac_backward_dsac_out* out) {
     if (!e || !out) return DSAC_ERR_ARG;
     return backward_dsac_run(e, n, out);
+}
+
+int dsac_gather_patches_device(dsac_engine* e, int32_t n, const uint8_t* d_frames, int32_t width, int32_t height,
+                               const int32_t* d_pix, int32_t pix_shared, float mean, float* d_patches, uint32_t* d_status,
+                               void* stream_v) {
+    if (!e) return DSAC_ERR_ARG;
+    if (n < 1 || !d_frames || !d_pix || !d_patches) return fail(e, DSAC_ERR_ARG, "dsac_gather_patches_device: bad arguments");
+    if (width < UP_PATCH || height < UP_PATCH) return fail(e, DSAC_ERR_ARG, "frame %dx%d smaller than a %d-pixel patch", width, height, UP_PATCH);
+    CU(cudaSetDevice(e->cfg.device));
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    GatherParams p;
+    p.frames = d_frames; p.width = width; p.height = height;
+    p.pix = d_pix; p.pix_stride = pix_shared ? 0 : DSAC_N * 2; p.n_cells = DSAC_N;
+    p.mean = mean; p.patches = d_patches; p.status = d_status;
+    if (d_status) CU(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(uint32_t), stream));
+    k_gather_patches<<<dim3(DSAC_N, n), UP_THREADS, 0, stream>>>(p);
+    e->launches++;
+    CU(cudaGetLastError());
+    return DSAC_OK;
+}
+
+int dsac_coords_from_prediction_device(dsac_engine* e, int32_t n, const float* d_prediction, int16_t* d_coords, void* stream_v) {
+    if (!e) return DSAC_ERR_ARG;
+    if (n < 1 || !d_prediction || !d_coords) return fail(e, DSAC_ERR_ARG, "dsac_coords_from_prediction_device: bad arguments");
+    CU(cudaSetDevice(e->cfg.device));
+    const size_t count = (size_t)n * DSAC_N * 3;
+    k_coords_from_prediction<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream_v>>>(d_prediction, d_coords, count);
+    e->launches++;
+    CU(cudaGetLastError());
+    return DSAC_OK;
 }
 
 int dsac_kabsch(dsac_engine* e, int32_t n, int32_t m, const double* a, const double* b, double* R, double* t) {

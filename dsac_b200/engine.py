@@ -20,7 +20,7 @@ ST_SAMPLER_EXHAUSTED, ST_REFINE_ABORTED = 1, 2
 EXPORTS = [
     "dsac_default_config", "dsac_engine_create", "dsac_engine_destroy", "dsac_last_error", "dsac_engine_config",
     "dsac_forward", "dsac_forward_submit", "dsac_forward_wait", "dsac_forward_device", "dsac_fetch", "dsac_device_view_get", "dsac_set_stages",
-    "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_kabsch",
+    "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_gather_patches_device", "dsac_coords_from_prediction_device", "dsac_kabsch",
     "dsac_stochastic_subsample",
     "dsac_synth_frames", "dsac_version",
 ]
@@ -107,6 +107,9 @@ def load(build_if_missing=True):
     lib.dsac_forward_dsac.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                       C.POINTER(DsacOut)]
     lib.dsac_backward_dsac.argtypes = [C.c_void_p, C.c_int32, C.POINTER(BackwardDsacOut)]
+    lib.dsac_gather_patches_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                               C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dsac_coords_from_prediction_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dsac_kabsch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dsac_stochastic_subsample.argtypes = [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]
     lib.dsac_synth_frames.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_int64, C.c_int32, C.c_double, C.c_double,
@@ -345,6 +348,17 @@ class Engine:
         res = BackwardDsacResult(n, self.cfg.n_hyps)
         self._check(self.lib.dsac_backward_dsac(self.h, n, C.byref(res.raw)))
         return res
+
+    def gather_patches_device(self, n, d_frames, width, height, d_pix, pix_shared, d_patches, mean=127.0, d_status=None, stream=None):
+        """dsac_gather_patches_device (raw device pointers as ints): BGR frames -> normalised 3x42x42 CNN patches."""
+        self._check(self.lib.dsac_gather_patches_device(self.h, n, C.c_void_p(d_frames), width, height, C.c_void_p(d_pix), pix_shared,
+                                                        C.c_float(mean), C.c_void_p(d_patches), C.c_void_p(d_status) if d_status else None,
+                                                        C.c_void_p(stream) if stream else None))
+
+    def coords_from_prediction_device(self, n, d_pred, d_coords, stream=None):
+        """dsac_coords_from_prediction_device: float metres -> int16 millimetres (cv::saturate_cast<short>)."""
+        self._check(self.lib.dsac_coords_from_prediction_device(self.h, n, C.c_void_p(d_pred), C.c_void_p(d_coords),
+                                                                C.c_void_p(stream) if stream else None))
 
     def kabsch(self, a, b):
         a = np.ascontiguousarray(a, np.float64)

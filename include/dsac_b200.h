@@ -43,6 +43,7 @@ extern "C" {
 
 /* per-frame status bits (dsac_forward_out.status) */
 #define DSAC_ST_SAMPLER_EXHAUSTED 1u      /* max_candidates reached before n_hyps accepts */
+#define DSAC_ST_BORDER_PATCH 4u           /* dsac_gather_patches_device met a border cell (the reference would skip it, cnn_softam.h:236-240) */
 #define DSAC_ST_REFINE_ABORTED 2u         /* refinement stopped early (<50 inliers / NaN), cnn_softam.h:1136,1147 */
 
 typedef struct dsac_engine dsac_engine;
@@ -215,6 +216,21 @@ typedef struct dsac_backward_dsac_out {
     int32_t* n_refine_jobs;   /* [n]        refine() evaluations of path I, nullable */
 } dsac_backward_dsac_out;
 int dsac_backward_dsac(dsac_engine* e, int32_t n_frames, dsac_backward_dsac_out* out);
+
+/* Upstream step on the device, so that frames never leave HBM between the image and the
+ * hypothesis engine.  All pointers are DEVICE pointers; `stream` is a cudaStream_t (NULL: default stream).
+ * dsac_gather_patches_device replaces the patch assembly of getCoordImg (cnn_softam.h:221-256) fused with forward()'s
+ * normalisation (lua/train_obj.lua:117-124, mean = 127) and pushMaps' layout (lua_calls.h:65-82):
+ *   patches[f][cell][c][y][x] = frames[f][oy-21+y][ox-21+x][c] - mean,   (ox, oy) = pix[f or 0][cell]
+ * frames: [n][height][width][3] uint8 BGR (jp::img_bgr_t); patches: [n][N][3][42][42] float.  A border cell (which
+ * stochasticSubSample never produces) yields a zero patch and DSAC_ST_BORDER_PATCH in status[f] (nullable).
+ * dsac_coords_from_prediction_device replaces "modeImg(y,x) = prediction[i] * 1000" (cnn_softam.h:262-268):
+ * prediction [n][N][3] float metres -> coords [n][N][3] int16 mm with cv::saturate_cast<short>. */
+int dsac_gather_patches_device(dsac_engine* e, int32_t n_frames, const uint8_t* d_frames, int32_t width, int32_t height,
+                               const int32_t* d_pix, int32_t pix_shared, float mean, float* d_patches, uint32_t* d_status,
+                               void* stream);
+int dsac_coords_from_prediction_device(dsac_engine* e, int32_t n_frames, const float* d_prediction, int16_t* d_coords,
+                                       void* stream);
 
 /* Batched Kabsch (Hypothesis::calcRigidBodyTransform, Hypothesis.cpp:145-200):
  * for each of n problems with m correspondences, b ~ R a + t.  a,b: [n][m][3] doubles. */

@@ -420,3 +420,30 @@ def bench_forward(cfg, coords, pix, n_threads=1, with_refine=False, want_avg=Fal
     avg = np.zeros((nf, 6)) if want_avg else None
     secs = lib().orc_bench_forward(C.byref(cfg), nf, _p(coords), _p(pix), int(n_threads), int(with_refine), _p(avg))
     return (secs, avg) if want_avg else secs
+
+
+# ---- upstream step, numpy restatement
+def gather_patches(frame_bgr, pix, mean=127.0, patch=42):
+    """getCoordImg's patch assembly (cnn_softam.h:221-256) + forward()'s normalisation (lua/train_obj.lua:117-124) in
+    pushMaps' channel-major order (lua_calls.h:65-82).  frame_bgr: [H][W][3] uint8; pix: [N][2] (origX, origY).
+    Returns float32 [N][3][42][42]; border cells (which the reference skips) come back as zero patches."""
+    frame_bgr = np.asarray(frame_bgr, np.uint8)
+    pix = np.asarray(pix).reshape(-1, 2)
+    Hh, W = frame_bgr.shape[:2]
+    half = patch // 2
+    out = np.zeros((pix.shape[0], 3, patch, patch), np.float32)
+    for i, (ox, oy) in enumerate(pix):
+        if ox < half or oy < half or ox > W - half or oy > Hh - half:
+            continue
+        p = frame_bgr[oy - half:oy + half, ox - half:ox + half, :].astype(np.float32)   # patch(curY-minY, curX-minX) = colorData(curY, curX)
+        out[i] = np.transpose(p, (2, 0, 1)) - np.float32(mean)
+    return out
+
+
+def coords_from_prediction(pred):
+    """modeImg(y, x) = prediction[i] * 1000 (cnn_softam.h:262-268): Vec3f * 1000 in float, then cv::saturate_cast<short>
+    (cvRound = round half to even via cvtss2si: NaN / out-of-int-range -> INT_MIN -> -32768)."""
+    v = np.asarray(pred, np.float32) * np.float32(1000.0)
+    bad = ~(np.abs(v) < np.float32(2147483648.0))
+    r = np.where(bad, -2147483648.0, np.rint(np.where(bad, 0, v).astype(np.float64)))
+    return np.clip(r, -32768, 32767).astype(np.int16)

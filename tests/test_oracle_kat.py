@@ -179,3 +179,20 @@ def test_backward_runs_and_is_finite(oracle, engine_mod):
     assert np.abs(bw.dloss_dobj).max() > 0
     # softmax-Jacobian gradients sum to zero (train_ransac_softam.cpp:361-376)
     assert abs(bw.score_grads.sum()) < 1e-9 * max(1.0, np.abs(bw.score_grads).max())
+
+
+def test_upstream_restatement_known_answers(oracle):
+    """Patch gather (cnn_softam.h:221-256 + train_obj.lua:117-124) and metres -> int16 mm (cnn_softam.h:262-268)."""
+    O = oracle
+    h, w = 60, 70
+    frame = (np.arange(h * w * 3) % 251).astype(np.uint8).reshape(h, w, 3)
+    pix = np.array([[21, 21], [w - 21, h - 21], [30, 25], [20, 30], [30, h - 20]])
+    p = O.gather_patches(frame, pix)
+    assert p.shape == (5, 3, 42, 42) and p.dtype == np.float32
+    # patch(c, y, x) = frame(oy - 21 + y, ox - 21 + x)[c] - 127
+    assert p[0, 0, 0, 0] == float(frame[0, 0, 0]) - 127 and p[0, 2, 41, 41] == float(frame[41, 41, 2]) - 127
+    assert p[1, 1, 41, 41] == float(frame[h - 1, w - 1, 1]) - 127            # last legal centre reaches the last pixel
+    assert p[2, 1, 3, 7] == float(frame[25 - 21 + 3, 30 - 21 + 7, 1]) - 127
+    assert (p[3] == 0).all() and (p[4] == 0).all()                          # border cells are skipped by the reference
+    c = O.coords_from_prediction(np.array([0.0005, 0.0015, 0.0025, -0.0015, 1.2344, 40.0, -40.0, np.nan, np.inf, 3e6], np.float32))
+    assert c.tolist() == [0, 2, 2, -2, 1234, 32767, -32768, -32768, -32768, -32768]   # half-to-even; cvtss2si overflow -> INT_MIN
