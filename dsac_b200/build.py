@@ -20,6 +20,8 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
     "-Xcompiler", "-O2", "-DDSAC_BUILD=1", "-DK1_THREADS_DEF=" + os.environ.get("DSAC_K1_THREADS", "384"),
     *(["-DK1_MIN_BLOCKS=" + os.environ["DSAC_K1_MIN_BLOCKS"]] if "DSAC_K1_MIN_BLOCKS" in os.environ else []),
+    *(["-DK4_THREADS_DEF=" + os.environ["DSAC_K4_THREADS"]] if "DSAC_K4_THREADS" in os.environ else []),
+    *(["-DK4_MIN_BLOCKS=" + os.environ["DSAC_K4_MIN_BLOCKS"]] if "DSAC_K4_MIN_BLOCKS" in os.environ else []),
 ]
 
 
@@ -44,11 +46,12 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, csrc=None):
+    """out / csrc: build a variant of the library somewhere else (tools/sweep.py); the product is LIB from CSRC."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-        [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + \
+        [os.path.join(csrc or CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -56,7 +59,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libdsac_b200.so")
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -81,6 +81,12 @@ struct dsac_engine {
     int pending_n = 0, pending_chunks = 0;
     BackwardScratch bw;
     cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // chunked H2D / compute / D2H pipeline of dsac_forward
+    // tail split (dsac_set_tail_split): the whole sampler waves of a batch run on a high-priority side stream, the
+    // frames of the last, partial wave on the caller's stream, so that scoring / refinement of the first part fill
+    // the SMs the partial wave leaves idle
+    cudaStream_t hi = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int tail_split = 1;
 };
 
 static int fail(dsac_engine* e, int code, const char* fmt, ...) {
@@ -142,6 +148,9 @@ void dsac_engine_destroy(dsac_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (cudaStream_t st : e->pipe)
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (e->hi) { cudaStreamSynchronize(e->hi); cudaStreamDestroy(e->hi); }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->d_phase) {
         unsigned long long h[16];
         if (cudaMemcpy(h, e->d_phase, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -260,6 +269,14 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
     }
     CUC(cudaMallocHost(&e->h_stream_ncand, n * cfg->n_streams * sizeof(long long)));
     for (int i = 0; i < 4; i++) CUC(cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking));
+    {
+        int least = 0, greatest = 0;
+        CUC(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUC(cudaStreamCreateWithPriority(&e->hi, cudaStreamNonBlocking, greatest));
+        CUC(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+        if (const char* ts = getenv("DSAC_TAIL_SPLIT")) e->tail_split = atoi(ts);
+    }
 #undef CUC
     *out = e;
     return DSAC_OK;
@@ -268,6 +285,13 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
 int dsac_set_stages(dsac_engine* e, uint32_t mask) {
     if (!e) return DSAC_ERR_ARG;
     e->stages = mask;
+    return DSAC_OK;
+}
+
+int dsac_set_tail_split(dsac_engine* e, int32_t mode) {
+    if (!e) return DSAC_ERR_ARG;
+    if (mode < 0 || mode > 2) return fail(e, DSAC_ERR_ARG, "tail split mode %d out of range [0,2]", mode);
+    e->tail_split = mode;
     return DSAC_OK;
 }
 
@@ -371,6 +395,33 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
     return DSAC_OK;
 }
 
+// forward_range over the whole batch, with the tail split: the sampler runs one CTA per (frame, stream) and
+// e->k1_slots CTAs are resident at a time, so a batch is a number of whole waves plus a partial one during which
+// most of every SM idles.  Frames [0, n1) (the whole waves) go to the high-priority side stream, the rest stays on
+// `stream`: the block scheduler dispatches the side stream's sampler CTAs first, its scoring / refinement kernels
+// then run next to the partial wave.  Fork / join with events, so for the caller everything still happens in
+// stream order on `stream`.  Frames are independent (disjoint slices of every engine buffer).
+static int forward_split(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* d_coords, const int32_t* d_pix,
+                         int32_t pix_shared, const double* d_gt_jp, cudaStream_t stream, bool allow_split) {
+    int32_t n1 = 0;
+    if (allow_split && e->tail_split && (e->stages & DSAC_STAGE_SAMPLE) && (e->stages & ~DSAC_STAGE_SAMPLE) && !e->hook) {
+        const int per_wave = e->k1_slots / std::max(1, e->cfg.n_streams);   // frames per sampler wave
+        if (per_wave >= 1 && n > per_wave && n % per_wave != 0) n1 = (n / per_wave) * per_wave;
+    }
+    if (n1 <= 0) return forward_range(e, 0, n, frame0, d_coords, d_pix, pix_shared, d_gt_jp, stream);
+    const size_t N = DSAC_N, f = (size_t)n1;
+    CU(cudaEventRecord(e->ev_fork, stream));
+    CU(cudaStreamWaitEvent(e->hi, e->ev_fork, 0));
+    int rc = forward_range(e, 0, n1, frame0, d_coords, d_pix, pix_shared, d_gt_jp, e->hi);
+    if (rc != DSAC_OK) return rc;
+    CU(cudaEventRecord(e->ev_join, e->hi));
+    rc = forward_range(e, n1, n - n1, frame0 + n1, d_coords + f * N * 3, pix_shared ? d_pix : d_pix + f * N * 2, pix_shared,
+                       d_gt_jp ? d_gt_jp + f * 12 : nullptr, stream);
+    if (rc != DSAC_OK) return rc;
+    CU(cudaStreamWaitEvent(stream, e->ev_join, 0));
+    return DSAC_OK;
+}
+
 int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* d_coords, const int32_t* d_pix,
                         int32_t pix_shared, const double* d_gt_jp, void* stream_v) {
     if (!e) return DSAC_ERR_ARG;
@@ -384,7 +435,7 @@ int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
     e->cur_n = n;
     e->dsac_n = 0;
     e->cur_frame0 = frame0;
-    return forward_range(e, 0, n, frame0, d_coords, d_pix, pix_shared, d_gt_jp, stream_v);
+    return forward_split(e, n, frame0, d_coords, d_pix, pix_shared, d_gt_jp, (cudaStream_t)stream_v, true);
 }
 
 // Queues the device->host copies of frames [off, off+n) into the caller's buffers (no synchronisation).
@@ -457,8 +508,8 @@ int dsac_device_view_get(dsac_engine* e, dsac_device_view* v) {
     return DSAC_OK;
 }
 
-int dsac_forward_submit(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
-                        int32_t pix_shared, const double* gt_jp, dsac_forward_out* out) {
+static int forward_submit_impl(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
+                               int32_t pix_shared, const double* gt_jp, dsac_forward_out* out, bool blocking) {
     if (!e) return DSAC_ERR_ARG;
     if (e->pending_chunks) return fail(e, DSAC_ERR_ARG, "dsac_forward_submit: the previous submitted pass has not been awaited");
     if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
@@ -505,8 +556,13 @@ int dsac_forward_submit(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
             CU(cudaMemcpyAsync(e->d_pix + f * N * 2, pix + f * N * 2, (size_t)m * N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         if (gt_jp) CU(cudaMemcpyAsync(e->d_gt + f * 12, gt_jp + f * 12, (size_t)m * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
         if (trace) cudaEventRecord(tev[1], st);
-        int rc = forward_range(e, lo, m, frame0 + lo, e->d_coords + f * N * 3, pix_shared ? e->d_pix : e->d_pix + f * N * 2,
-                               pix_shared, gt_jp ? e->d_gt + f * 12 : nullptr, st);
+        // one chunk: the tail split applies (mode 1: blocking calls only -- with several passes in flight the other
+        // pass already fills the partial wave and a high-priority stream would only delay it; mode 2: always)
+        int rc = (chunks == 1)
+                     ? forward_split(e, m, frame0, e->d_coords, e->d_pix, pix_shared, gt_jp ? e->d_gt : nullptr, st,
+                                     blocking ? e->tail_split >= 1 : e->tail_split >= 2)
+                     : forward_range(e, lo, m, frame0 + lo, e->d_coords + f * N * 3, pix_shared ? e->d_pix : e->d_pix + f * N * 2,
+                                     pix_shared, gt_jp ? e->d_gt + f * 12 : nullptr, st);
         if (rc != DSAC_OK) return rc;
         if (trace) cudaEventRecord(tev[2], st);
         if (out) {
@@ -541,9 +597,14 @@ int dsac_forward_wait(dsac_engine* e) {
     return DSAC_OK;
 }
 
+int dsac_forward_submit(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
+                        int32_t pix_shared, const double* gt_jp, dsac_forward_out* out) {
+    return forward_submit_impl(e, n, frame0, coords, pix, pix_shared, gt_jp, out, false);
+}
+
 int dsac_forward(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
                  int32_t pix_shared, const double* gt_jp, dsac_forward_out* out) {
-    int rc = dsac_forward_submit(e, n, frame0, coords, pix, pix_shared, gt_jp, out);
+    int rc = forward_submit_impl(e, n, frame0, coords, pix, pix_shared, gt_jp, out, true);
     if (rc != DSAC_OK) return rc;
     return dsac_forward_wait(e);
 }

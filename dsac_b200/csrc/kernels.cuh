@@ -574,7 +574,7 @@ struct ScoreParams {
 };
 
 constexpr int K2_THREADS = 320;  // 10 warps x 5 points per thread = 1600 scene coordinates
-constexpr int K2_PTS = 5;   // (the one-reciprocal sigmoid sum in k_score is written out for exactly 5)
+constexpr int K2_PTS = 5;   // (the paired-reciprocal sigmoid sum in k_score is written out for exactly 5)
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_MAX_TILE = 256;
 
@@ -652,6 +652,96 @@ __device__ void softargmax_tail(const ScoreParams& p, int frame, double* s_red /
     }
 }
 
+// One warp's share of a tile: the warp's 160 scene coordinates (5 per thread, in registers) against the tile's nh
+// hypotheses (3x4 rows in shared memory), 8 hypotheses at a time; writes the error matrix and leaves the warp's
+// partial soft-inlier sums in part[0..nh).
+//
+// Per (hypothesis, point): ONE rsqrt gives the clamped reprojection error,
+//   e = |pix - proj| = sqrt(A)/|z|,  A = (pu*z - xs)^2 + (pv*z - ys)^2  ->  e = A * rsqrt(A * z^2).
+// q = A z^2 vanishes only for a point exactly on its pixel (A = 0, e = 0) or exactly in the camera plane (z = 0,
+// where cv::projectPoints substitutes 1/z := 1).  GUARDED = false evaluates the formula without those two selects
+// per pair and only records (one FSETP per 5 pairs) whether the smallest q of the thread's five points left the
+// normal range; the caller then repeats the warp's tile with GUARDED = true, which overwrites everything the
+// unguarded pass wrote.  Returns that flag.
+//
+// Soft inlier sigma(beta (tau - e)) = 1 / (1 + t), t = 2^(kbeta (e - tau)) <= 2^65 since e <= 100.  Two sigmoids share
+// one reciprocal, 1/w0 + 1/w1 = (w0 + w1) / (w0 w1): the product overflows only when both sigmoids are below 2^-63,
+// and then the quotient is (w0 + w1) * 0 = 0 -- no clamp needed.
+template <bool WRITE_DM, bool GUARDED>
+__device__ __forceinline__ bool score_tile(const float* s_P, int nh, const float (&X)[K2_PTS], const float (&Y)[K2_PTS],
+                                           const float (&Z)[K2_PTS], const float (&pu)[K2_PTS], const float (&pv)[K2_PTS],
+                                           float* dm, float kbeta, float tau_k, float* part, int tid, int lane) {
+    static_assert(K2_PTS == 5, "the sigmoid pairing is written out for 5 points per thread");
+    bool rare = false;
+    for (int hb = 0; hb < nh; hb += 8) {
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int h = hb + u;
+            float a = 0.f;
+            if (h < nh) {
+                const float4 r0 = *reinterpret_cast<const float4*>(s_P + h * 12);
+                const float4 r1 = *reinterpret_cast<const float4*>(s_P + h * 12 + 4);
+                const float4 r2 = *reinterpret_cast<const float4*>(s_P + h * 12 + 8);
+                float e[K2_PTS], q[K2_PTS];
+#pragma unroll
+                for (int j = 0; j < K2_PTS; j++) {
+                    const float xs = fmaf(r0.x, X[j], fmaf(r0.y, Y[j], fmaf(r0.z, Z[j], r0.w)));
+                    const float ys = fmaf(r1.x, X[j], fmaf(r1.y, Y[j], fmaf(r1.z, Z[j], r1.w)));
+                    float zs = fmaf(r2.x, X[j], fmaf(r2.y, Y[j], fmaf(r2.z, Z[j], r2.w)));
+                    if (GUARDED) zs = (zs != 0.f) ? zs : 1.f;  // z ? 1/z : 1 (cv::projectPoints)
+                    const float du = fmaf(pu[j], zs, -xs);
+                    const float dv = fmaf(pv[j], zs, -ys);
+                    const float A = fmaf(du, du, dv * dv);
+                    q[j] = A * (zs * zs);
+                    e[j] = fminf(A * fast_rsqrt(q[j]), DSAC_MAXINPUT_F);  // min(norm, CNN_OBJ_MAXINPUT), cnn_softam.h:357
+                    if (GUARDED) e[j] = (A > 0.f) ? e[j] : 0.f;
+                }
+                if (!GUARDED) rare |= !(fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])), q[4]) >= 1.17549435e-38f);
+                float w[K2_PTS];
+#pragma unroll
+                for (int j = 0; j < K2_PTS; j++) {
+                    if (WRITE_DM) __stcs(dm + (size_t)h * DSAC_N_CONST + tid + j * K2_THREADS, e[j]);
+                    w[j] = 1.f + fast_ex2(fmaf(kbeta, e[j], -tau_k));
+                }
+                a = (w[0] + w[1]) * fast_rcp(w[0] * w[1]);
+                a = fmaf(w[2] + w[3], fast_rcp(w[2] * w[3]), a);
+                a += fast_rcp(w[4]);
+            }
+            acc[u] = a;
+        }
+        // transposed warp reduction: 8 partials -> lane (4*b4+2*b3+b2) group holds hypothesis sum
+#pragma unroll
+        for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (i < half) {
+                    float send = up ? acc[i] : acc[i + half];
+                    float keep = up ? acc[i + half] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+        }
+        float v = acc[0];
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if ((lane & 3) == 0) {
+            int u = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if (hb + u < nh) part[hb + u] = v;
+        }
+    }
+    return rare;
+}
+
+// the guarded repeat is kept out of line: it runs (practically) never
+template <bool WRITE_DM>
+__device__ __noinline__ void score_tile_guarded(const float* s_P, int nh, const float (&X)[K2_PTS], const float (&Y)[K2_PTS],
+                                                const float (&Z)[K2_PTS], const float (&pu)[K2_PTS], const float (&pv)[K2_PTS],
+                                                float* dm, float kbeta, float tau_k, float* part, int tid, int lane) {
+    score_tile<WRITE_DM, true>(s_P, nh, X, Y, Z, pu, pv, dm, kbeta, tau_k, part, tid, lane);
+}
+
 template <bool WRITE_DM>
 __global__ void __launch_bounds__(K2_THREADS, 3) k_score(ScoreParams p) {
     __shared__ __align__(16) float s_P[K2_MAX_TILE * 12];
@@ -691,66 +781,10 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k_score(ScoreParams p) {
 
         float* dm = WRITE_DM ? p.diffmaps + ((size_t)frame * p.H + hbeg) * DSAC_N_CONST : nullptr;
         const float tau_k = p.thr * p.kbeta;
-
-        for (int hb = 0; hb < nh; hb += 8) {
-            float acc[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int h = hb + u;
-                float a = 0.f;
-                if (h < nh) {
-                    const float4 r0 = *reinterpret_cast<const float4*>(s_P + h * 12);
-                    const float4 r1 = *reinterpret_cast<const float4*>(s_P + h * 12 + 4);
-                    const float4 r2 = *reinterpret_cast<const float4*>(s_P + h * 12 + 8);
-                    // Per point: ONE rsqrt gives the clamped reprojection error,
-                    //   e = |pix - proj| = sqrt(A)/|z|,  A = (pu*z - xs)^2 + (pv*z - ys)^2  ->  e = A * rsqrt(A * z^2),
-                    // and the thread's five sigmoids share ONE reciprocal (below),  t = 2^(kbeta*(e - tau)) clamped to 2^25.
-                    float t[K2_PTS];
-#pragma unroll
-                    for (int j = 0; j < K2_PTS; j++) {
-                        float xs = fmaf(r0.x, X[j], fmaf(r0.y, Y[j], fmaf(r0.z, Z[j], r0.w)));
-                        float ys = fmaf(r1.x, X[j], fmaf(r1.y, Y[j], fmaf(r1.z, Z[j], r1.w)));
-                        float zs = fmaf(r2.x, X[j], fmaf(r2.y, Y[j], fmaf(r2.z, Z[j], r2.w)));
-                        zs = (zs != 0.f) ? zs : 1.f;  // z ? 1/z : 1 (cv::projectPoints)
-                        float du = fmaf(pu[j], zs, -xs);
-                        float dv = fmaf(pv[j], zs, -ys);
-                        float A = fmaf(du, du, dv * dv);
-                        float e = A * fast_rsqrt(A * (zs * zs));
-                        e = (A > 0.f) ? fminf(e, DSAC_MAXINPUT_F) : 0.f;  // min(norm, CNN_OBJ_MAXINPUT), cnn_softam.h:357
-                        if (WRITE_DM) __stcs(dm + (size_t)h * DSAC_N_CONST + tid + j * K2_THREADS, e);
-                        t[j] = fminf(fast_ex2(fmaf(p.kbeta, e, -tau_k)), 33554432.f);
-                    }
-                    {
-                        // all five sigmoids over ONE reciprocal: sum_j 1/u_j = N/D with u_j = 1 + t_j <= 2^25 + 1, so D < 2^126
-                        // (a sigmoid below 2^-25 is rounded up to 2^-25: <= 5e-6 absolute on a score, far inside tolerance)
-                        float u0 = 1.f + t[0], u1 = 1.f + t[1], u2 = 1.f + t[2], u3 = 1.f + t[3], u4 = 1.f + t[4];
-                        float p01 = u0 * u1, p23 = u2 * u3, q = p23 * u4;
-                        float N = fmaf(u0 + u1, q, p01 * fmaf(u2 + u3, u4, p23));
-                        a = N * fast_rcp(p01 * q);
-                    }
-                }
-                acc[u] = a;
-            }
-            // transposed warp reduction: 8 partials -> lane (4*b4+2*b3+b2) group holds hypothesis sum
-#pragma unroll
-            for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i < half) {
-                        float send = up ? acc[i] : acc[i + half];
-                        float keep = up ? acc[i + half] : acc[i];
-                        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
-                }
-            }
-            float v = acc[0];
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((lane & 3) == 0) {
-                int u = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                if (hb + u < nh) s_part[warp][hb + u] = v;
-            }
+        const bool rare = score_tile<WRITE_DM, false>(s_P, nh, X, Y, Z, pu, pv, dm, p.kbeta, tau_k, s_part[warp], tid, lane);
+        if (__any_sync(0xffffffffu, rare)) {
+            __syncwarp();
+            score_tile_guarded<WRITE_DM>(s_P, nh, X, Y, Z, pu, pv, dm, p.kbeta, tau_k, s_part[warp], tid, lane);
         }
         __syncthreads();
         // fixed-order cross-warp sum -> score (double from here on, like the reference's vector<double>)

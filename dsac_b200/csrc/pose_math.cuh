@@ -97,6 +97,64 @@ DSAC_HD void project_point(const double R[9], const double t[3], double X, doubl
     *v = y * f + cy;
 }
 
+// ----------------------------------------------------------------------------- reprojection error of one cell
+// Separately rounded double operations (no FMA contraction), as the scalar code of cv::projectPoints.
+#if defined(__CUDA_ARCH__)
+#define DSAC_DMUL(a, b) __dmul_rn((a), (b))
+#define DSAC_DADD(a, b) __dadd_rn((a), (b))
+#define DSAC_DDIV(a, b) __ddiv_rn((a), (b))
+#define DSAC_FSUB(a, b) __fsub_rn((a), (b))
+#else
+#define DSAC_DMUL(a, b) ((a) * (b))
+#define DSAC_DADD(a, b) ((a) + (b))
+#define DSAC_DDIV(a, b) ((a) / (b))
+#define DSAC_FSUB(a, b) ((a) - (b))
+#endif
+
+// One entry of getDiffMap (cnn_softam.h:319-362) with the reference's roundings: projection in double, rounded
+// to a float Point2f, float difference to the float pixel, norm in double, clamp at 100, stored as float.
+DSAC_HD float reproj_error_exact(const double R[9], const double t[3], double X, double Y, double Z, double f, double cx,
+                                 double cy, float pix_u, float pix_v) {
+    double x = DSAC_DADD(DSAC_DADD(DSAC_DADD(DSAC_DMUL(R[0], X), DSAC_DMUL(R[1], Y)), DSAC_DMUL(R[2], Z)), t[0]);
+    double y = DSAC_DADD(DSAC_DADD(DSAC_DADD(DSAC_DMUL(R[3], X), DSAC_DMUL(R[4], Y)), DSAC_DMUL(R[5], Z)), t[1]);
+    double z = DSAC_DADD(DSAC_DADD(DSAC_DADD(DSAC_DMUL(R[6], X), DSAC_DMUL(R[7], Y)), DSAC_DMUL(R[8], Z)), t[2]);
+    z = z ? DSAC_DDIV(1., z) : 1;
+    x = DSAC_DMUL(x, z);
+    y = DSAC_DMUL(y, z);
+    const float pu = (float)DSAC_DADD(DSAC_DMUL(x, f), cx), pv = (float)DSAC_DADD(DSAC_DMUL(y, f), cy);
+    const float du = DSAC_FSUB(pix_u, pu), dv = DSAC_FSUB(pix_v, pv);
+    const double nrm = sqrt(DSAC_DADD(DSAC_DMUL((double)du, (double)du), DSAC_DMUL((double)dv, (double)dv)));
+    return (float)fmin(nrm, 100.0);
+}
+
+// Conservative fp32 version of "reproj_error_exact(...) < thr" for the refinement's inlier test (the only use the
+// refinement makes of its error maps, cnn_softam.h:1125-1133).  P = rows (f R0 | f t0), (f R1 | f t1), (R2 | t2)
+// rounded to float; pu, pv = pixel - principal point; c_abs = |cx| + |cy|.  Returns 1 / 0 when the decision is
+// certain, -1 when the fp32 error is within its own error bound of the threshold (the caller then evaluates
+// reproj_error_exact).  Bound: every fp32 sum s = sum_k P_k X_k carries at most 4 roundings of 2^-24 relative to
+// S = sum_k |P_k X_k| (2.4e-7 S; 1e-6 S is used), which propagate to e = |(pu z - x, pv z - y)| / |z| as
+// [dx + dy + (|pu| + |pv| + e) dz] / |z|; the reference's own float rounding of the projected pixel adds
+// 6e-8 (|u| + |v|).  NaN / infinity (z = 0) compare false and therefore return -1.
+DSAC_HD int reproj_below_thr_fast(const float* P, float X, float Y, float Z, float pu, float pv, float c_abs, float thr) {
+    const float xs = fmaf(P[0], X, fmaf(P[1], Y, fmaf(P[2], Z, P[3])));
+    const float ys = fmaf(P[4], X, fmaf(P[5], Y, fmaf(P[6], Z, P[7])));
+    const float zs = fmaf(P[8], X, fmaf(P[9], Y, fmaf(P[10], Z, P[11])));
+    const float aX = fabsf(X), aY = fabsf(Y), aZ = fabsf(Z);
+    const float Sx = fmaf(fabsf(P[0]), aX, fmaf(fabsf(P[1]), aY, fmaf(fabsf(P[2]), aZ, fabsf(P[3]))));
+    const float Sy = fmaf(fabsf(P[4]), aX, fmaf(fabsf(P[5]), aY, fmaf(fabsf(P[6]), aZ, fabsf(P[7]))));
+    const float Sz = fmaf(fabsf(P[8]), aX, fmaf(fabsf(P[9]), aY, fmaf(fabsf(P[10]), aZ, fabsf(P[11]))));
+    const float az = fabsf(zs), apu = fabsf(pu), apv = fabsf(pv);
+    const float du = fmaf(pu, zs, -xs), dv = fmaf(pv, zs, -ys);
+    const float e = sqrtf(fmaf(du, du, dv * dv)) / az;
+    const float bound = 1e-6f * (Sx + Sy + (apu + apv + e) * Sz) / az + 2.4e-7f * (apu + apv + c_abs + 2.f * e) + 1e-5f * e + 1e-4f;
+#ifdef DSAC_REPROJ_BOUND_SCALE   /* test aid: how far can the bound shrink before a decision goes wrong */
+    if (!(fabsf(e - thr) > (float)(DSAC_REPROJ_BOUND_SCALE) * bound)) return -1;
+#else
+    if (!(fabsf(e - thr) > bound)) return -1;
+#endif
+    return e < thr ? 1 : 0;
+}
+
 // ----------------------------------------------------------------------------- P3P
 // Largest real root of y^3 + a2 y^2 + a1 y + a0 (the resolvent cubic of Ferrari's method).
 #if defined(__CUDA_ARCH__)

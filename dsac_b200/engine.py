@@ -20,7 +20,7 @@ ST_SAMPLER_EXHAUSTED, ST_REFINE_ABORTED = 1, 2
 EXPORTS = [
     "dsac_default_config", "dsac_engine_create", "dsac_engine_destroy", "dsac_last_error", "dsac_engine_config",
     "dsac_forward", "dsac_forward_submit", "dsac_forward_wait", "dsac_forward_device", "dsac_fetch", "dsac_device_view_get", "dsac_set_stages",
-    "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_gather_patches_device", "dsac_coords_from_prediction_device", "dsac_kabsch",
+    "dsac_set_tail_split", "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_gather_patches_device", "dsac_coords_from_prediction_device", "dsac_kabsch",
     "dsac_stochastic_subsample",
     "dsac_synth_frames", "dsac_version",
 ]
@@ -79,11 +79,15 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    path = _build.LIB
+    alt = os.environ.get("DSAC_B200_LIB")   # development aid (tools/sweep.py): another BUILD of the same CUDA library
+    if alt:
+        path = alt
+    elif build_if_missing:
         _build.build()
-    if not os.path.exists(_build.LIB):
-        raise RuntimeError("libdsac_b200.so is missing: build it with `python -m dsac_b200.build` (no CPU fallback exists)")
-    lib = C.CDLL(_build.LIB)
+    if not os.path.exists(path):
+        raise RuntimeError("%s is missing: build it with `python -m dsac_b200.build` (no CPU fallback exists)" % path)
+    lib = C.CDLL(path)
     lib.dsac_last_error.restype = C.c_char_p
     lib.dsac_last_error.argtypes = [C.c_void_p]
     lib.dsac_version.restype = C.c_char_p
@@ -101,6 +105,7 @@ def load(build_if_missing=True):
     lib.dsac_fetch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ForwardOut), C.c_void_p]
     lib.dsac_device_view_get.argtypes = [C.c_void_p, C.POINTER(DeviceView)]
     lib.dsac_set_stages.argtypes = [C.c_void_p, C.c_uint32]
+    lib.dsac_set_tail_split.argtypes = [C.c_void_p, C.c_int32]
     lib.dsac_set_score_hook.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dsac_backward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.POINTER(BackwardOut)]
@@ -262,6 +267,10 @@ class Engine:
 
     def set_stages(self, mask):
         self._check(self.lib.dsac_set_stages(self.h, mask))
+
+    def set_tail_split(self, mode):
+        """0: off, 1: forward_device + blocking forward (default), 2: submitted passes too (scheduling only)."""
+        self._check(self.lib.dsac_set_tail_split(self.h, mode))
 
     def forward(self, coords, pix, gt_jp=None, frame0=0, want_diffmaps=False, out=None):
         """dsac_forward with HOST buffers (numpy arrays)."""

@@ -27,7 +27,7 @@ def host_shim():
     d = os.path.join(ROOT, "tests", "host_shim")
     so = os.path.join(d, "libhost_shim.so")
     src = os.path.join(d, "host_math_shim.cpp")
-    deps = [src] + [os.path.join(ROOT, "dsac_b200", "csrc", f) for f in ("pose_math.cuh", "sampler.cuh")]
+    deps = [src] + [os.path.join(ROOT, "dsac_b200", "csrc", f) for f in ("pose_math.cuh", "sampler.cuh", "lm_math.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])

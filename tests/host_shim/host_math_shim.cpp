@@ -112,3 +112,73 @@ extern "C" void shim_filter_reasons(long long out[24]) {
     for (int k = 0; k < 24; k++) out[k] = -1;
 #endif
 }
+
+// Inlier test of the refinement (k_refine): the conservative fp32 decision against the reference's exact
+// arithmetic on n cells of one pose.  out = {decided 0/1, undecided, wrong decisions (must be 0), exact inliers}.
+extern "C" void shim_reproj_check(int n, const double* rvec, const double* tvec, const int16_t* coords, const int32_t* pix,
+                                  double f, double cx, double cy, int thr, long long out[4], float* exact_err /* n or null */) {
+    double R[9];
+    dsac::rodrigues_v2m(rvec, R);
+    float P[12];
+    for (int row = 0; row < 3; row++)
+        for (int col = 0; col < 4; col++) {
+            double v = col < 3 ? R[row * 3 + col] : tvec[row];
+            P[row * 4 + col] = (float)(row < 2 ? f * v : v);
+        }
+    const float cxf = (float)cx, cyf = (float)cy, c_abs = fabsf(cxf) + fabsf(cyf), thrf = (float)thr;
+    for (int k = 0; k < 4; k++) out[k] = 0;
+    for (int i = 0; i < n; i++) {
+        const float X = (float)coords[i * 3], Y = (float)coords[i * 3 + 1], Z = (float)coords[i * 3 + 2];
+        const float fu = (float)pix[i * 2], fv = (float)pix[i * 2 + 1];
+        const float e = dsac::reproj_error_exact(R, tvec, X, Y, Z, f, cx, cy, fu, fv);
+        if (exact_err) exact_err[i] = e;
+        const bool inl = e < thrf;
+        const int r = dsac::reproj_below_thr_fast(P, X, Y, Z, fu - cxf, fv - cyf, c_abs, thrf);
+        if (r < 0) out[1]++;
+        else {
+            out[0]++;
+            if ((r != 0) != inl) out[2]++;
+        }
+        out[3] += inl;
+    }
+}
+
+// ---- the refinement's Levenberg-Marquardt arithmetic (lm_math.cuh), run sequentially on the host
+#include "../../dsac_b200/csrc/lm_math.cuh"
+extern "C" {
+void shim_lm_solve6_fast(const double* S27, double lambda, double* x) { dsac::lm_solve6_fast(S27, lambda, x); }
+void shim_rodrigues_jac(const double* r, double* R, double* J) { dsac::rodrigues_jac(r, R, J); }
+void shim_rodrigues_jac_lanes(const double* r, double* R, double* J) {
+    for (int lane = 0; lane < 32; lane++) dsac::rodrigues_jac_warp(r, lane, R, J);
+}
+// k_refine's LM loop with the lanes / threads of the kernel run one after the other: same helper functions, same
+// state machine, same buffers.  obj [n][3], img [n][2] floats; pose (rvec, tvec) in/out; returns the iteration count.
+int shim_lm_refine(int n, const float* obj, const float* img, double f, double cx, double cy, double* pose, int* n_passes) {
+    double s_R[9], s_J[27], s_param[6], s_prev[6], s_sum[2][32];
+    for (int k = 0; k < 6; k++) s_param[k] = pose[k];
+    for (int lane = 0; lane < 32; lane++) dsac::rodrigues_jac_warp(s_param, lane, s_R, s_J);
+    dsac::LMState lm;
+    int passes = 0;
+    for (;;) {
+        double v[32];
+        for (int k = 0; k < 32; k++) v[k] = 0;
+        for (int i = 0; i < n; i++)
+            dsac::lm_point_contrib(s_R, s_J, s_param, obj[i * 3], obj[i * 3 + 1], obj[i * 3 + 2], img[i * 2], img[i * 2 + 1], f, cx, cy, v);
+        passes++;
+        const int buf = dsac::lm_next_buf(lm);
+        for (int k = 0; k < 32; k++) s_sum[buf][k] = v[k];
+        const int action = dsac::lm_advance(lm, buf, s_sum[buf][27], s_param, s_prev);
+        if (action == dsac::LM_DONE) break;
+        if (action == dsac::LM_SOLVE_NEWBASE)
+            for (int k = 0; k < 6; k++) s_prev[k] = s_param[k];
+        double x[6], trial[6];
+        dsac::lm_solve6_fast(s_sum[lm.cur], dsac::c_lm_lambda[lm.lambdaLg10 + 16], x);
+        for (int k = 0; k < 6; k++) trial[k] = s_prev[k] - x[k];
+        for (int k = 0; k < 6; k++) s_param[k] = trial[k];
+        for (int lane = 0; lane < 32; lane++) dsac::rodrigues_jac_warp(trial, lane, s_R, s_J);
+    }
+    for (int k = 0; k < 6; k++) pose[k] = s_param[k];
+    if (n_passes) *n_passes = passes;
+    return lm.iters;
+}
+}

@@ -246,3 +246,63 @@ def test_submit_wait_equals_blocking_forward(engine_mod):
     ref = E.Engine(max_frames=6, n_hyps=32).forward(coords, pix, gt_jp)
     for k in ("img_idx", "cand_idx", "ref_pose", "avg_pose", "sf", "loss", "n_candidates"):
         assert np.array_equal(np.concatenate([getattr(ra, k), getattr(rb, k)]), getattr(ref, k)), k
+
+
+@pytest.mark.parametrize("T,H,n", [(8, 32, 40), (1, 16, 300)])
+def test_tail_split_is_scheduling_only(engine_mod, T, H, n):
+    """dsac_set_tail_split moves the frames of the sampler's last, partial wave to another stream: every output
+    must be bit-identical with the split off, on (blocking call, device-resident call) and on for submitted passes."""
+    import torch
+    E = engine_mod
+    coords, pix, gt_cv, gt_jp = E.synth_frames(n, n_streams=T)
+    keys = ("img_idx", "cand_idx", "hyp_pose", "scores", "sf", "avg_pose", "ref_pose", "inlier_map", "loss", "n_candidates", "status")
+    eng = E.Engine(max_frames=n, n_streams=T, n_hyps=H)
+    eng.set_tail_split(0)
+    ref = eng.forward(coords, pix, gt_jp, want_diffmaps=True)
+    eng.set_tail_split(1)
+    got = eng.forward(coords, pix, gt_jp, want_diffmaps=True)
+    for k in keys + ("diffmaps",):
+        assert np.array_equal(getattr(ref, k), getattr(got, k)), k
+    eng.set_tail_split(2)
+    sub = eng.forward_submit(coords, pix, gt_jp)
+    eng.forward_wait()
+    for k in keys:
+        assert np.array_equal(getattr(ref, k), getattr(sub, k)), k
+    # device-resident inputs on the caller's stream
+    eng.set_tail_split(1)
+    d_c, d_p, d_g = torch.from_numpy(coords).cuda(), torch.from_numpy(pix).cuda(), torch.from_numpy(gt_jp).cuda()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        eng.forward_device(n, d_c.data_ptr(), d_p.data_ptr(), 0, d_g.data_ptr(), 0, st.cuda_stream)
+        dev = eng.fetch(n, stream=st.cuda_stream)
+    for k in keys:
+        assert np.array_equal(getattr(ref, k), getattr(dev, k)), k
+    with pytest.raises(RuntimeError):
+        eng.set_tail_split(7)
+    eng.close()
+
+
+def test_points_in_the_camera_plane_and_on_their_pixel(engine_mod, oracle):
+    """k_score's unguarded error formula hands a warp to the guarded form when A z^2 leaves the normal range: z = 0
+    exactly (cv::projectPoints then uses 1/z := 1) or a point exactly on its pixel.  All-outlier frame with a bounded
+    sampler -> zero poses (R = I, t = 0), scene coordinates (0, 0, 0) and (x, y, 0) -> z = 0 for those cells."""
+    E, O = engine_mod, oracle
+    coords, pix, gt_cv, gt_jp = E.synth_frames(1, rho=0.0)
+    coords = coords.copy()
+    coords[0, ::3] = 0                       # projects to the principal point: error = |pixel - (cx, cy)|, < 100 near the centre
+    coords[0, 1::11, 2] = 0                  # z = 0 with non-zero x, y
+    eng = E.Engine(max_frames=1, max_candidates=1024, n_hyps=8)
+    res = eng.forward(coords, pix, gt_jp, want_diffmaps=True)
+    cfg = O.default_config(n_hyps=8, max_candidates=1024)
+    fw = O.forward(cfg, coords[0], pix[0], gt_jp[0, :9], gt_jp[0, 9:])
+    assert np.array_equal(fw.img_idx, res.img_idx[0])
+    zero = np.flatnonzero((res.img_idx[0] < 0).all(1))
+    assert len(zero) > 0, "the test needs at least one value-encoded (zero) pose"
+    d = np.hypot(pix[0][::3, 0] - 320.0, pix[0][::3, 1] - 240.0)
+    want = np.minimum(d, 100.0).astype(np.float32)
+    for h in zero:
+        assert np.abs(res.diffmaps[0][h].reshape(-1)[::3] - want).max() <= 1e-4
+    assert (res.diffmaps[0][zero].reshape(len(zero), -1)[:, ::3].min(1) < 100.0).all()
+    assert np.abs(fw.diffmaps - res.diffmaps[0]).max() <= 2e-3
+    assert np.abs(fw.scores - res.scores[0]).max() <= 1e-5 * max(1e-30, np.abs(fw.scores).max())
+    eng.close()
