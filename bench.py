@@ -303,6 +303,7 @@ def main():
 
     # ---- per-stage kernel durations (stage-isolated launches, CUDA events) and the K2 roofline
     stage_ms = {}
+    eng.set_tail_split(0)      # one launch per stage over the whole batch (the timed steps above ran with the tail split on)
     for name, mask in (("k_sample", E.STAGE_SAMPLE), ("k_score", E.STAGE_SCORE), ("k_refine", E.STAGE_REFINE | E.STAGE_EVAL)):
         eng.set_stages(E.STAGE_ALL)
         step_device()
@@ -311,6 +312,9 @@ def main():
         torch.cuda.synchronize()
         stage_ms[name] = timed_steps(step_device, max(3, min(args.steps, 10))) / max(3, min(args.steps, 10))
     eng.set_stages(E.STAGE_ALL)
+    step_device(); torch.cuda.synchronize()
+    serial_ms = timed_steps(step_device, max(3, min(args.steps, 10))) / max(3, min(args.steps, 10))   # whole step, tail split off
+    eng.set_tail_split(1)
     peak, peak_src = peaks()
     k2_s = stage_ms["k_score"] * 1e-3
     achieved = BYTES_M * nf / k2_s / 1e9
@@ -454,6 +458,8 @@ def main():
                        "frames_per_gpu": nf, "n_hyps": H, "points": NPTS, "streams_per_frame": 1, "inlier_ratio": 0.5,
                        "noise_mm": 25.0, "data_seed": 20170721, "sampler_seed": 1305, "alpha": 0.1, "beta": 0.5,
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+                       "tail_split": "on (dsac_set_tail_split 1): the frames of the sampler's last, partial wave run on the caller's stream, the "
+                                     "whole waves on a high-priority side stream; %.3f ms/step with it off" % serial_ms,
                        "l2": "256 MB buffer written between timed steps (flush); each step also streams %.2f GB of diffmaps" % (BYTES_M * nf / 1e9)},
             "e2e": {"value": e2e_value, "unit": "hyp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(t[0].item()) / args.steps,
@@ -468,8 +474,8 @@ def main():
             "gpu_launches": gpu_launches,
             "roofline": roofline,
             "kernels_ms": stage_ms,
-            "sampler": {"kernel": "k_sample (73 % of the step; fp64-latency / barrier-bound, no HBM or tensor roofline applies: "
-                                  "ncu fp64 pipe 32 %, issue 47 %, see profiles/r01_k_sample_full.txt)",
+            "sampler": {"kernel": "k_sample (%.0f %% of the stage-isolated step; fp64-latency / barrier-bound, no HBM or tensor roofline applies: "
+                                  "see profiles/r01_k_sample_full.txt)" % (100 * stage_ms["k_sample"] / ssum),
                         "candidates_per_s": quality["candidates_per_frame"] * nf / (stage_ms["k_sample"] * 1e-3),
                         "candidates_per_accepted_hypothesis": quality["candidates_per_frame"] / H,
                         "ms_per_launch": stage_ms["k_sample"]},

@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     *(["-DK1_MIN_BLOCKS=" + os.environ["DSAC_K1_MIN_BLOCKS"]] if "DSAC_K1_MIN_BLOCKS" in os.environ else []),
     *(["-DK4_THREADS_DEF=" + os.environ["DSAC_K4_THREADS"]] if "DSAC_K4_THREADS" in os.environ else []),
     *(["-DK4_MIN_BLOCKS=" + os.environ["DSAC_K4_MIN_BLOCKS"]] if "DSAC_K4_MIN_BLOCKS" in os.environ else []),
+    *os.environ.get("DSAC_EXTRA_NVCC_FLAGS", "").split(),   # experiments (tools/sweep.py)
 ]
 
 

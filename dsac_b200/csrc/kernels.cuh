@@ -658,79 +658,102 @@ __device__ void softargmax_tail(const ScoreParams& p, int frame, double* s_red /
 //
 // Per (hypothesis, point): ONE rsqrt gives the clamped reprojection error,
 //   e = |pix - proj| = sqrt(A)/|z|,  A = (pu*z - xs)^2 + (pv*z - ys)^2  ->  e = A * rsqrt(A * z^2).
-// q = A z^2 vanishes only for a point exactly on its pixel (A = 0, e = 0) or exactly in the camera plane (z = 0,
-// where cv::projectPoints substitutes 1/z := 1).  GUARDED = false evaluates the formula without those two selects
-// per pair and only records (one FSETP per 5 pairs) whether the smallest q of the thread's five points left the
-// normal range; the caller then repeats the warp's tile with GUARDED = true, which overwrites everything the
-// unguarded pass wrote.  Returns that flag.
+// A z^2 vanishes for a point exactly on its pixel (A = 0 -> e = 0 through the floor under the rsqrt) or exactly in the
+// camera plane (z = 0, where cv::projectPoints substitutes 1/z := 1).  GUARDED = false evaluates the formula without
+// the select on z and only records (one FSETP per 5 pairs) whether one of the thread's five z is exactly 0; the
+// caller then repeats the warp's tile with GUARDED = true, which overwrites everything the unguarded pass wrote.
+// Returns that flag.
 //
 // Soft inlier sigma(beta (tau - e)) = 1 / (1 + t), t = 2^(kbeta (e - tau)) <= 2^65 since e <= 100.  Two sigmoids share
 // one reciprocal, 1/w0 + 1/w1 = (w0 + w1) / (w0 w1): the product overflows only when both sigmoids are below 2^-63,
 // and then the quotient is (w0 + w1) * 0 = 0 -- no clamp needed.
+// One group of up to 8 hypotheses starting at hb.  FULL = all 8 exist: no per-hypothesis branch, so the eight bodies
+// form one basic block and the instruction scheduler can overlap the MUFU tail (rsqrt, ex2, rcp: 13 per hypothesis,
+// 8 issue cycles each on the XU pipe) of one hypothesis with the FMA-pipe projection of the next -- with a branch
+// between hypotheses the warps of a CTA, which run in step, all queue on the XU pipe at the same time.
+template <bool WRITE_DM, bool GUARDED, bool FULL>
+__device__ __forceinline__ bool score_group8(const float* s_P, int hb, int nh, const float (&X)[K2_PTS], const float (&Y)[K2_PTS],
+                                             const float (&Z)[K2_PTS], const float (&pu)[K2_PTS], const float (&pv)[K2_PTS],
+                                             float* dm, float kbeta, float tau_k, float* part, int tid, int lane) {
+    bool rare = false;
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int h = hb + u;
+        float a = 0.f;
+        if (FULL || h < nh) {
+            const float4 r0 = *reinterpret_cast<const float4*>(s_P + h * 12);
+            const float4 r1 = *reinterpret_cast<const float4*>(s_P + h * 12 + 4);
+            const float4 r2 = *reinterpret_cast<const float4*>(s_P + h * 12 + 8);
+            float e[K2_PTS], az[K2_PTS];
+#pragma unroll
+            for (int j = 0; j < K2_PTS; j++) {
+                const float xs = fmaf(r0.x, X[j], fmaf(r0.y, Y[j], fmaf(r0.z, Z[j], r0.w)));
+                const float ys = fmaf(r1.x, X[j], fmaf(r1.y, Y[j], fmaf(r1.z, Z[j], r1.w)));
+                float zs = fmaf(r2.x, X[j], fmaf(r2.y, Y[j], fmaf(r2.z, Z[j], r2.w)));
+                az[j] = fabsf(zs);
+                if (GUARDED) zs = (zs != 0.f) ? zs : 1.f;  // z ? 1/z : 1 (cv::projectPoints)
+                const float du = fmaf(pu[j], zs, -xs);
+                const float dv = fmaf(pv[j], zs, -ys);
+                const float A = fmaf(du, du, dv * dv);
+                // A = 0 (the float projection lands exactly on the pixel -- it does happen for the three points a P3P pose
+                // fits exactly): 0 * rsqrt(floor) = 0.  A > 0 implies A >= ulp^2 and z != 0 implies z^2 far above the floor.
+                e[j] = fminf(A * fast_rsqrt(fmaxf(A * (zs * zs), 1e-30f)), DSAC_MAXINPUT_F);  // min(norm, CNN_OBJ_MAXINPUT), cnn_softam.h:357
+            }
+            if (!GUARDED) rare |= (fminf(fminf(fminf(az[0], az[1]), fminf(az[2], az[3])), az[4]) == 0.f);
+            float w[K2_PTS];
+#pragma unroll
+            for (int j = 0; j < K2_PTS; j++) {
+                if (WRITE_DM) __stcs(dm + (size_t)h * DSAC_N_CONST + tid + j * K2_THREADS, e[j]);
+                w[j] = 1.f + fast_ex2(fmaf(kbeta, e[j], -tau_k));
+            }
+#if defined(K2_SIGMOID5)
+            {   // (experiment) all five sigmoids over ONE reciprocal, t clamped to 2^25 so that the product stays below 2^126
+                float u0 = fminf(w[0], 33554433.f), u1 = fminf(w[1], 33554433.f), u2 = fminf(w[2], 33554433.f), u3 = fminf(w[3], 33554433.f), u4 = fminf(w[4], 33554433.f);
+                float p01 = u0 * u1, p23 = u2 * u3, qq = p23 * u4;
+                float Nn = fmaf(u0 + u1, qq, p01 * fmaf(u2 + u3, u4, p23));
+                a = Nn * fast_rcp(p01 * qq);
+            }
+#else
+            a = (w[0] + w[1]) * fast_rcp(w[0] * w[1]);
+            a = fmaf(w[2] + w[3], fast_rcp(w[2] * w[3]), a);
+            a += fast_rcp(w[4]);
+#endif
+        }
+        acc[u] = a;
+    }
+    // transposed warp reduction: 8 partials -> lane (4*b4+2*b3+b2) group holds hypothesis sum
+#pragma unroll
+    for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (i < half) {
+                float send = up ? acc[i] : acc[i + half];
+                float keep = up ? acc[i + half] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+    }
+    float v = acc[0];
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if ((lane & 3) == 0) {
+        int u = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        if (FULL || hb + u < nh) part[hb + u] = v;
+    }
+    return rare;
+}
+
 template <bool WRITE_DM, bool GUARDED>
 __device__ __forceinline__ bool score_tile(const float* s_P, int nh, const float (&X)[K2_PTS], const float (&Y)[K2_PTS],
                                            const float (&Z)[K2_PTS], const float (&pu)[K2_PTS], const float (&pv)[K2_PTS],
                                            float* dm, float kbeta, float tau_k, float* part, int tid, int lane) {
     static_assert(K2_PTS == 5, "the sigmoid pairing is written out for 5 points per thread");
     bool rare = false;
-    for (int hb = 0; hb < nh; hb += 8) {
-        float acc[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int h = hb + u;
-            float a = 0.f;
-            if (h < nh) {
-                const float4 r0 = *reinterpret_cast<const float4*>(s_P + h * 12);
-                const float4 r1 = *reinterpret_cast<const float4*>(s_P + h * 12 + 4);
-                const float4 r2 = *reinterpret_cast<const float4*>(s_P + h * 12 + 8);
-                float e[K2_PTS], q[K2_PTS];
-#pragma unroll
-                for (int j = 0; j < K2_PTS; j++) {
-                    const float xs = fmaf(r0.x, X[j], fmaf(r0.y, Y[j], fmaf(r0.z, Z[j], r0.w)));
-                    const float ys = fmaf(r1.x, X[j], fmaf(r1.y, Y[j], fmaf(r1.z, Z[j], r1.w)));
-                    float zs = fmaf(r2.x, X[j], fmaf(r2.y, Y[j], fmaf(r2.z, Z[j], r2.w)));
-                    if (GUARDED) zs = (zs != 0.f) ? zs : 1.f;  // z ? 1/z : 1 (cv::projectPoints)
-                    const float du = fmaf(pu[j], zs, -xs);
-                    const float dv = fmaf(pv[j], zs, -ys);
-                    const float A = fmaf(du, du, dv * dv);
-                    q[j] = A * (zs * zs);
-                    e[j] = fminf(A * fast_rsqrt(q[j]), DSAC_MAXINPUT_F);  // min(norm, CNN_OBJ_MAXINPUT), cnn_softam.h:357
-                    if (GUARDED) e[j] = (A > 0.f) ? e[j] : 0.f;
-                }
-                if (!GUARDED) rare |= !(fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])), q[4]) >= 1.17549435e-38f);
-                float w[K2_PTS];
-#pragma unroll
-                for (int j = 0; j < K2_PTS; j++) {
-                    if (WRITE_DM) __stcs(dm + (size_t)h * DSAC_N_CONST + tid + j * K2_THREADS, e[j]);
-                    w[j] = 1.f + fast_ex2(fmaf(kbeta, e[j], -tau_k));
-                }
-                a = (w[0] + w[1]) * fast_rcp(w[0] * w[1]);
-                a = fmaf(w[2] + w[3], fast_rcp(w[2] * w[3]), a);
-                a += fast_rcp(w[4]);
-            }
-            acc[u] = a;
-        }
-        // transposed warp reduction: 8 partials -> lane (4*b4+2*b3+b2) group holds hypothesis sum
-#pragma unroll
-        for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (i < half) {
-                    float send = up ? acc[i] : acc[i + half];
-                    float keep = up ? acc[i + half] : acc[i];
-                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-        }
-        float v = acc[0];
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        if ((lane & 3) == 0) {
-            int u = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-            if (hb + u < nh) part[hb + u] = v;
-        }
-    }
+    int hb = 0;
+    for (; hb + 8 <= nh; hb += 8) rare |= score_group8<WRITE_DM, GUARDED, true>(s_P, hb, nh, X, Y, Z, pu, pv, dm, kbeta, tau_k, part, tid, lane);
+    if (hb < nh) rare |= score_group8<WRITE_DM, GUARDED, false>(s_P, hb, nh, X, Y, Z, pu, pv, dm, kbeta, tau_k, part, tid, lane);
     return rare;
 }
 
@@ -742,8 +765,11 @@ __device__ __noinline__ void score_tile_guarded(const float* s_P, int nh, const 
     score_tile<WRITE_DM, true>(s_P, nh, X, Y, Z, pu, pv, dm, kbeta, tau_k, part, tid, lane);
 }
 
+#ifndef K2_MIN_BLOCKS
+#define K2_MIN_BLOCKS 3
+#endif
 template <bool WRITE_DM>
-__global__ void __launch_bounds__(K2_THREADS, 3) k_score(ScoreParams p) {
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_BLOCKS) k_score(ScoreParams p) {
     __shared__ __align__(16) float s_P[K2_MAX_TILE * 12];
     __shared__ float s_part[K2_WARPS][K2_MAX_TILE];
     __shared__ double s_red[8 * K2_WARPS];

@@ -255,22 +255,30 @@ DSAC_HD void rodrigues_jac_warp(const double r[3], int lane, double* sR, double*
 struct LMState {
     int lambdaLg10 = -3, iters = 0, cur = 0;
     bool have_cur = false;
-    double prevErrNorm = 1.7976931348623157e308;
+    double prevErr2 = 0;   // squared error norm at the base vector (CvLevMarq keeps prevErrNorm = its square root)
 };
 enum { LM_DONE = 0, LM_SOLVE_KEEP = 1, LM_SOLVE_NEWBASE = 2 };
 
 DSAC_HD int lm_next_buf(const LMState& st) { return st.have_cur ? (st.cur ^ 1) : 0; }
 
 // err2: squared error norm of the pass just made (at `param`); prev: the base vector.
+// The reference compares square roots (errNorm > prevErrNorm, |param - prev| / |prev| < FLT_EPSILON); both tests are
+// decided on the squares whenever those differ from equality by more than a few ulps (sqrt is monotone, the three
+// roundings of the quotient are bounded by 2 ulps) and evaluated literally otherwise, so the decisions are identical
+// while the sqrt / divide latency leaves the common path.
 DSAC_HD int lm_advance(LMState& st, int buf, double err2, const double* param, const double* prev) {
     if (!st.have_cur) {   // CALC_J at the initial parameters
         st.have_cur = true;
         st.cur = buf;
-        st.prevErrNorm = sqrt(err2);
+        st.prevErr2 = err2;
         return LM_SOLVE_NEWBASE;
     }
-    const double errNorm = sqrt(err2);   // CHECK_ERR at the trial parameters
-    if (errNorm > st.prevErrNorm && ++st.lambdaLg10 <= 16) return LM_SOLVE_KEEP;
+    // CHECK_ERR at the trial parameters
+    bool worse;
+    if (err2 > st.prevErr2 * (1 + 4e-15)) worse = true;
+    else if (!(err2 > st.prevErr2)) worse = false;          // a <= b (or NaN)  =>  !(sqrt(a) > sqrt(b))
+    else worse = sqrt(err2) > sqrt(st.prevErr2);
+    if (worse && ++st.lambdaLg10 <= 16) return LM_SOLVE_KEEP;
     st.lambdaLg10 = st.lambdaLg10 - 1 > -16 ? st.lambdaLg10 - 1 : -16;
     double dn = 0, pn = 0;
     for (int k = 0; k < 6; k++) {
@@ -278,9 +286,13 @@ DSAC_HD int lm_advance(LMState& st, int buf, double err2, const double* param, c
         dn += d * d;
         pn += prev[k] * prev[k];
     }
-    const double change = sqrt(dn) / sqrt(pn);
-    if (++st.iters >= 20 || change < 1.1920928955078125e-07) return LM_DONE;
-    st.prevErrNorm = errNorm;   // accepted: the pass just made is the next CALC_J
+    const double eps2pn = 1.4210854715202004e-14 * pn;      // FLT_EPSILON^2 = 2^-46, exact
+    bool small;
+    if (dn < eps2pn * (1 - 1e-14)) small = true;
+    else if (dn > eps2pn * (1 + 1e-14)) small = false;
+    else small = sqrt(dn) / sqrt(pn) < 1.1920928955078125e-07;
+    if (++st.iters >= 20 || small) return LM_DONE;
+    st.prevErr2 = err2;   // accepted: the pass just made is the next CALC_J
     st.cur = buf;
     return LM_SOLVE_NEWBASE;
 }

@@ -130,11 +130,15 @@ DSAC_HD float reproj_error_exact(const double R[9], const double t[3], double X,
 // Conservative fp32 version of "reproj_error_exact(...) < thr" for the refinement's inlier test (the only use the
 // refinement makes of its error maps, cnn_softam.h:1125-1133).  P = rows (f R0 | f t0), (f R1 | f t1), (R2 | t2)
 // rounded to float; pu, pv = pixel - principal point; c_abs = |cx| + |cy|.  Returns 1 / 0 when the decision is
-// certain, -1 when the fp32 error is within its own error bound of the threshold (the caller then evaluates
-// reproj_error_exact).  Bound: every fp32 sum s = sum_k P_k X_k carries at most 4 roundings of 2^-24 relative to
-// S = sum_k |P_k X_k| (2.4e-7 S; 1e-6 S is used), which propagate to e = |(pu z - x, pv z - y)| / |z| as
-// [dx + dy + (|pu| + |pv| + e) dz] / |z|; the reference's own float rounding of the projected pixel adds
-// 6e-8 (|u| + |v|).  NaN / infinity (z = 0) compare false and therefore return -1.
+// certain, -1 when the fp32 error e = |(pu z - x, pv z - y)| / |z| is within its own error bound B of the threshold
+// (the caller then evaluates reproj_error_exact).
+//   Bound: every fp32 sum s = sum_k P_k X_k carries at most 4 roundings of 2^-24 relative to S = sum_k |P_k X_k|
+//   (2.4e-7 S; 1e-6 S is used), which propagate to e as [dx + dy + (|pu| + |pv| + e) dz] / |z|; the reference's own
+//   float rounding of the projected pixel adds 6e-8 (|u| + |v|); e is replaced by T = 2 thr inside B (for e > T the
+//   decision "not below" only needs B < thr, which is required).
+//   The test is made on squares, multiplied through by |z| (no sqrt, no division):
+//       sqrt(A) < thr |z| - B |z|  ->  below,     sqrt(A) > thr |z| + B |z|  ->  not below.
+// NaN / a bound that is not small against the threshold (z ~ 0) return -1.
 DSAC_HD int reproj_below_thr_fast(const float* P, float X, float Y, float Z, float pu, float pv, float c_abs, float thr) {
     const float xs = fmaf(P[0], X, fmaf(P[1], Y, fmaf(P[2], Z, P[3])));
     const float ys = fmaf(P[4], X, fmaf(P[5], Y, fmaf(P[6], Z, P[7])));
@@ -143,16 +147,22 @@ DSAC_HD int reproj_below_thr_fast(const float* P, float X, float Y, float Z, flo
     const float Sx = fmaf(fabsf(P[0]), aX, fmaf(fabsf(P[1]), aY, fmaf(fabsf(P[2]), aZ, fabsf(P[3]))));
     const float Sy = fmaf(fabsf(P[4]), aX, fmaf(fabsf(P[5]), aY, fmaf(fabsf(P[6]), aZ, fabsf(P[7]))));
     const float Sz = fmaf(fabsf(P[8]), aX, fmaf(fabsf(P[9]), aY, fmaf(fabsf(P[10]), aZ, fabsf(P[11]))));
-    const float az = fabsf(zs), apu = fabsf(pu), apv = fabsf(pv);
+    const float az = fabsf(zs), apuv = fabsf(pu) + fabsf(pv), T = 2.f * thr;
     const float du = fmaf(pu, zs, -xs), dv = fmaf(pv, zs, -ys);
-    const float e = sqrtf(fmaf(du, du, dv * dv)) / az;
-    const float bound = 1e-6f * (Sx + Sy + (apu + apv + e) * Sz) / az + 2.4e-7f * (apu + apv + c_abs + 2.f * e) + 1e-5f * e + 1e-4f;
+    const float A = fmaf(du, du, dv * dv);
+    const float c1 = 1e-6f * (Sx + Sy + (apuv + T) * Sz);
+    const float k3 = fmaf(2.4e-7f, apuv + c_abs, fmaf(1.05e-5f, T, 2e-4f));
 #ifdef DSAC_REPROJ_BOUND_SCALE   /* test aid: how far can the bound shrink before a decision goes wrong */
-    if (!(fabsf(e - thr) > (float)(DSAC_REPROJ_BOUND_SCALE) * bound)) return -1;
+    const float Bz = (float)(DSAC_REPROJ_BOUND_SCALE) * fmaf(k3, az, c1);
 #else
-    if (!(fabsf(e - thr) > bound)) return -1;
+    const float Bz = fmaf(k3, az, c1);                  // B |z|
 #endif
-    return e < thr ? 1 : 0;
+    const float taz = thr * az;
+    if (!(Bz < 0.5f * taz)) return -1;
+    const float lo = taz - Bz, hi = taz + Bz;
+    if (A < lo * lo) return 1;
+    if (A > hi * hi) return 0;
+    return -1;
 }
 
 // ----------------------------------------------------------------------------- P3P

@@ -124,6 +124,10 @@ __device__ double max_loss_dev(const double R1[9], const double t1[3], const dou
 //            solves the damped 6x6 system in registers and builds the next R / dR/dr across its lanes.  Two block
 //            barriers per trial.
 __global__ void __launch_bounds__(K4_THREADS, K4_MIN_BLOCKS) k_refine(RefineParams p) {
+    // the frame's scene coordinates (int16 mm, this job's perturbation applied) and pixel positions, staged once per job:
+    // every refinement step reads all of them for the inlier flags and the selected ones in each LM pass
+    __shared__ short s_cX[DSAC_N_CONST], s_cY[DSAC_N_CONST], s_cZ[DSAC_N_CONST];
+    __shared__ float s_fu[DSAC_N_CONST], s_fv[DSAC_N_CONST];
     __shared__ uint32_t s_bits[DSAC_N_CONST / 32];
     __shared__ unsigned char s_imap[DSAC_N_CONST];
     __shared__ unsigned short s_sel[K4_MAX_INLIERS];
@@ -147,14 +151,19 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MIN_BLOCKS) k_refine(RefinePara
     const int step_limit = p.job_max_steps ? min(p.ref_steps, p.job_max_steps[job])
                                            : (p.max_steps ? min(p.ref_steps, p.max_steps[frame]) : p.ref_steps);
 
-    auto coord = [&](int c, int k) -> float {
-        int v = __ldg(coords + c * 3 + k);
-        if (c * 3 + k == pert_idx) v = (int)(short)(v + pert_delta);  // short += float eps (cnn_softam.h:887)
-        return (float)v;
-    };
-
     if (tid < 6) s_pose[tid] = p.job_init[(size_t)job * 6 + tid];
-    for (int i = tid; i < DSAC_N_CONST; i += K4_THREADS) s_imap[i] = 0;
+    for (int i = tid; i < DSAC_N_CONST; i += K4_THREADS) {
+        s_imap[i] = 0;
+        int v[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            v[k] = __ldg(coords + i * 3 + k);
+            if (i * 3 + k == pert_idx) v[k] = (int)(short)(v[k] + pert_delta);  // short += float eps (cnn_softam.h:887)
+        }
+        s_cX[i] = (short)v[0]; s_cY[i] = (short)v[1]; s_cZ[i] = (short)v[2];
+        s_fu[i] = (float)__ldg(pix + i * 2);
+        s_fv[i] = (float)__ldg(pix + i * 2 + 1);
+    }
     __syncthreads();
 
     const float thrf = (float)p.thr;
@@ -185,8 +194,8 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MIN_BLOCKS) k_refine(RefinePara
             const int c = base + tid;
             bool flag = false;
             if (c < DSAC_N_CONST) {
-                const float X = coord(c, 0), Y = coord(c, 1), Z = coord(c, 2);
-                const float fu = (float)__ldg(pix + c * 2), fv = (float)__ldg(pix + c * 2 + 1);
+                const float X = (float)s_cX[c], Y = (float)s_cY[c], Z = (float)s_cZ[c];
+                const float fu = s_fu[c], fv = s_fv[c];
                 const int r = reproj_below_thr_fast(P, X, Y, Z, fu - cxf, fv - cyf, c_abs, thrf);
                 if (r >= 0) {
                     flag = (r != 0);
@@ -204,17 +213,30 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MIN_BLOCKS) k_refine(RefinePara
         __syncthreads();
     };
 
+    // this thread's selected points of the current refinement step (constant over its LM loop), loaded once
+    constexpr int K4_PPT = (K4_MAX_INLIERS + K4_THREADS - 1) / K4_THREADS;
+    float selX[K4_PPT], selY[K4_PPT], selZ[K4_PPT], selU[K4_PPT], selV[K4_PPT];
+    auto load_selected = [&](int n) {
+#pragma unroll
+        for (int k = 0; k < K4_PPT; k++) {
+            const int i = tid + k * K4_THREADS;
+            const int c = (i < n) ? s_sel[i] : 0;
+            selX[k] = (float)s_cX[c]; selY[k] = (float)s_cY[c]; selZ[k] = (float)s_cZ[c];
+            selU[k] = s_fu[c]; selV[k] = s_fv[c];
+        }
+    };
+
     // per-thread contribution of the selected points to [0..20] upper triangle of JtJ, [21..26] JtErr, [27] |err|^2
     // at (s_param, s_R, s_J), reduced over the block into s_red[warp][0..31] (lane L holds sum L)
     auto normal_equations_pass = [&](int n) {
         double v[32];
 #pragma unroll
         for (int k = 0; k < 32; k++) v[k] = 0;
-        for (int i = tid; i < n; i += K4_THREADS) {
-            const int c = s_sel[i];
-            lm_point_contrib(s_R, s_J, s_param, (double)coord(c, 0), (double)coord(c, 1), (double)coord(c, 2),
-                             (double)(float)__ldg(pix + c * 2), (double)(float)__ldg(pix + c * 2 + 1), p.f, p.cx, p.cy, v);
-        }
+#pragma unroll
+        for (int k = 0; k < K4_PPT; k++)
+            if (tid + k * K4_THREADS < n)
+                lm_point_contrib(s_R, s_J, s_param, (double)selX[k], (double)selY[k], (double)selZ[k], (double)selU[k], (double)selV[k],
+                                 p.f, p.cx, p.cy, v);
         // transposed butterfly: after the step with offset `off` every lane keeps half of its values; lane L ends with sum L
 #pragma unroll
         for (int half = 16, off = 16; half >= 1; half >>= 1, off >>= 1) {
@@ -258,6 +280,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MIN_BLOCKS) k_refine(RefinePara
         if (count < 50) break;  // cnn_softam.h:1136
 
         // ---- Levenberg-Marquardt, CvLevMarq(6, 2n, max_iter 20, eps FLT_EPSILON)
+        load_selected(count);
         // (state used by warp 0 only, uniform across its lanes; trial / base parameter vectors live in s_param / s_prev)
         LMState lm;
         if (warp == 0) {

@@ -13,3 +13,4 @@ for _ in range(reps):
     eng.forward_device(nb, dc.data_ptr(), dp.data_ptr(), 0, dg.data_ptr(), 0, st)
 torch.cuda.synchronize()
 print("done", eng.launches)
+eng.close()

@@ -4,7 +4,7 @@
     python tools/sweep.py run            # on the GPU box: one tools/sweep_one.py process per variant -> gpurun_out/sweep.jsonl
 
 Variants: the kernels of the last commit ("old": kernels.cuh / refine.cuh from git HEAD with the current host code),
-and the working tree's kernels with several k_refine block sizes.  Development aid only."""
+and the working tree's kernels with experiment macros.  Development aid only."""
 import os
 import shutil
 import subprocess
@@ -12,7 +12,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VAR = os.path.join(ROOT, "variants")
-K4 = [("k4_64x8", "64", "8"), ("k4_128x4", "128", "4"), ("k4_32x16", "32", "16"), ("k4_96x5", "96", "5"), ("k4_64x6", "64", "6")]
+# (name, extra nvcc flags)
+VARIANTS = [("cur", ""), ("k4_128x4", "-DK4_THREADS_DEF=128 -DK4_MIN_BLOCKS=4"), ("k2_sig5", "-DK2_SIGMOID5=1")]
 
 
 def build():
@@ -27,8 +28,8 @@ def build():
                 fh.write(subprocess.check_output(["git", "-C", ROOT, "show", os.environ["SWEEP_OLD_REF"] + ":dsac_b200/csrc/" + f]))
         subprocess.check_call([sys.executable, "-c", code, os.path.join(VAR, "old.so"), old])
         print("built old.so")
-    for name, thr, mb in K4:
-        env = dict(os.environ, DSAC_K4_THREADS=thr, DSAC_K4_MIN_BLOCKS=mb)
+    for name, flags in VARIANTS:
+        env = dict(os.environ, DSAC_EXTRA_NVCC_FLAGS=flags)
         subprocess.check_call([sys.executable, "-c", code, os.path.join(VAR, name + ".so"), ""], env=env)
         print("built", name)
 
