@@ -43,6 +43,8 @@ struct BackwardScratch {
     double* hypjp = nullptr;         // [n][H][39]  R(9) t(3) J(27) of every hypothesis in jp convention
     double* row = nullptr;           // [n][N*3]  dLoss_dObj_1row
     double* drefobj = nullptr;       // [n][6][N*3] (diagnostic, optional)
+    double* part = nullptr;          // [n][groups][N*3] partial rows of k_dscore
+    int groups = 1;
 };
 inline void backward_scratch_free(BackwardScratch* s) {
     if (s->buf) cudaFree(s->buf);
@@ -125,6 +127,10 @@ struct BwParams {
     const double* ref_pose;     // [n][6]
     const int32_t* inlier_map;  // [n][N]
     BackwardScratch s;
+    // k_dscore splits the hypotheses of a frame over `groups` CTAs; group g accumulates into part[frame][g][N*3]
+    // (zeroed by the caller) and k_dscore_reduce adds the groups to s.row in order
+    double* part;
+    int groups;
 };
 
 // ------------------------------------------------------------------ DSAC / RANSAC variant (train_ransac.cpp:304-381)
@@ -186,33 +192,64 @@ __global__ void k_dsac_job_p3p(DsacBwParams p) {
 
 // path I: dLoss_dObj(idx, c) += sf_h * (dLossMax(refined_h, gt) . dRefine_h)(idx*3+c), hypotheses and columns in the
 // reference's order (one thread per frame: the sums are reproducible)
-__global__ void k_dsac_combine(DsacBwParams p) {
-    const int frame = blockIdx.x * blockDim.x + threadIdx.x;
+// path I of the DSAC variant: row[col] += sf_h * dLossMax_h . (refine(+eps) - refine(-eps)) / (2 eps) * scale over the
+// central-difference pairs of a frame, in pair order (pairs are sorted by hypothesis; a hypothesis touches a column at
+// most once, so within one hypothesis' run the additions are independent, and the runs are applied one after the other).
+// One warp per frame: first the lanes evaluate dLossMax of the frame's selected hypotheses in parallel, then the runs
+// are walked in order with the lanes spread over a run's pairs.
+constexpr int DSAC_COMBINE_MAX_HYPS = 1024;   // = DSAC_MAX_HYPS
+__global__ void __launch_bounds__(32) k_dsac_combine(DsacBwParams p) {
+    __shared__ int s_run_begin[DSAC_COMBINE_MAX_HYPS + 1];
+    __shared__ double s_dl[32][7];                       // dLossMax (1x6) and sf of 32 runs' hypotheses at a time
+    const int frame = blockIdx.x, lane = threadIdx.x;
     if (frame >= p.n_frames) return;
     double* row = p.path1 + (size_t)frame * DSAC_N_CONST * 3;
+    const int q_begin = p.frame_pair_begin[frame], q_end = p.frame_pair_begin[frame + 1];
+    // runs of equal hypothesis
+    int n_runs = 0;
+    for (int q0 = q_begin; q0 < q_end; q0 += 32) {
+        const int q = q0 + lane;
+        const bool start = q < q_end && (q == q_begin || p.pair_hyp[q] != p.pair_hyp[q - 1]);
+        const unsigned m = __ballot_sync(0xffffffffu, start);
+        if (start) {
+            const int r = n_runs + __popc(m & ((1u << lane) - 1u));
+            if (r < DSAC_COMBINE_MAX_HYPS) s_run_begin[r] = q;
+        }
+        n_runs += __popc(m);
+    }
+    n_runs = min(n_runs, DSAC_COMBINE_MAX_HYPS);
+    if (lane == 0) s_run_begin[n_runs] = q_end;
+    __syncwarp();
+    // dLossMax of every run's hypothesis
     const double* g = p.gt_jp + (size_t)frame * 12;
     double gt6[6];
     rodrigues_m2v(g, gt6);
     gt6[3] = g[9]; gt6[4] = g[10]; gt6[5] = g[11];
-    int cur = -1;
-    double dl[6] = {0, 0, 0, 0, 0, 0}, sf = 0;
-    for (int q = p.frame_pair_begin[frame]; q < p.frame_pair_begin[frame + 1]; q++) {
-        const int hyp = p.pair_hyp[q];
-        if (hyp != cur) {
-            cur = hyp;
-            double ref6[6];
+    for (int r0 = 0; r0 < n_runs; r0 += 32) {
+        if (r0 + lane < n_runs) {
+            const int hyp = p.pair_hyp[s_run_begin[r0 + lane]];
+            double ref6[6], dl[6];
             jp6_from_cv_dev(p.ref_pose + (size_t)hyp * 6, ref6);
             dloss_max_dev(ref6, gt6, dl);
-            sf = p.sf[hyp];
+            for (int k = 0; k < 6; k++) s_dl[lane][k] = dl[k];
+            s_dl[lane][6] = p.sf[hyp];
         }
-        const double* fS = p.job_jp6 + (size_t)(2 * q) * 6;
-        const double* bS = fS + 6;
-        const double scale = (double)p.pair_scale[q];
-        double acc = 0;
-        for (int k = 0; k < 6; k++) acc += dl[k] * ((fS[k] - bS[k]) / 4.0 * scale);   // / (2 * eps), eps = 2; * skip
-        row[p.pair_col[q]] += sf * acc;
+        __syncwarp();
+        for (int r = r0; r < min(n_runs, r0 + 32); r++) {
+            const double sf = s_dl[r - r0][6];
+            for (int q = s_run_begin[r] + lane; q < s_run_begin[r + 1]; q += 32) {
+                const double* fS = p.job_jp6 + (size_t)(2 * q) * 6;
+                const double* bS = fS + 6;
+                const double scale = (double)p.pair_scale[q];
+                double acc = 0;
+                for (int k = 0; k < 6; k++) acc += s_dl[r - r0][k] * ((fS[k] - bS[k]) / 4.0 * scale);   // / (2 * eps), eps = 2; * skip
+                row[p.pair_col[q]] += sf * acc;
+            }
+            __syncwarp();   // the next run may touch the same columns
+        }
     }
 }
+
 
 // ---- per frame: dLossMax and the refine job list (one warp, lane 0 does the serial scan)
 __global__ void k_bw_prep(BwParams p, int n) {
@@ -435,18 +472,42 @@ __global__ void k_bw_scatter_pnp(BwParams p, int n) {
     }
 }
 
-// ---- dScore (cnn_softam.h:564-646): thread = scene coordinate, loop over hypotheses.
+// ---- dScore (cnn_softam.h:564-646): thread = scene coordinate, loop over a group of the frame's hypotheses.
+// grid (groups, frames): with one CTA per frame a training batch of 16..64 frames left most of the 148 SMs idle for the
+// dominant kernel of the backward pass.  Every addition into a group's partial row is ordered (barriers of the h loop),
+// and the groups are added in order, so the gradient is run-to-run reproducible.
 constexpr int K5_THREADS = 320, K5_PTS = 5, K5_WARPS = K5_THREADS / 32;
+constexpr int K5_MAX_GROUPS = 32;
+
+// hypothesis groups for n frames: enough CTAs for ~4 per SM, at most K5_MAX_GROUPS, at least 8 hypotheses each
+inline int dscore_groups(int n_frames, int n_hyps, int sm_count) {
+    int g = (4 * sm_count + n_frames - 1) / std::max(1, n_frames);
+    g = std::min(g, K5_MAX_GROUPS);
+    g = std::min(g, std::max(1, n_hyps / 8));
+    return std::max(1, g);
+}
+
+__global__ void k_dscore_reduce(BwParams p) {
+    const int frame = blockIdx.x;
+    double* row = p.s.row + (size_t)frame * DSAC_N_CONST * 3;
+    const double* part = p.part + (size_t)frame * p.groups * DSAC_N_CONST * 3;
+    for (int c = threadIdx.x; c < DSAC_N_CONST * 3; c += blockDim.x) {
+        double s = row[c];
+        for (int g = 0; g < p.groups; g++) s += part[(size_t)g * DSAC_N_CONST * 3 + c];
+        row[c] = s;
+    }
+}
 
 __global__ void __launch_bounds__(K5_THREADS) k_dscore(BwParams p) {
     __shared__ double s_h[39];
     __shared__ double s_red[K5_WARPS][6];
     __shared__ double s_w[6];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int frame = blockIdx.x;
+    const int frame = blockIdx.y, group = blockIdx.x;
+    const int per_group = (p.H + p.groups - 1) / p.groups, h_begin = group * per_group, h_end = min(p.H, h_begin + per_group);
     const int16_t* coords = p.coords + (size_t)frame * DSAC_N_CONST * 3;
     const int32_t* pix = p.pix + (size_t)frame * p.pix_stride;
-    double* row = p.s.row + (size_t)frame * DSAC_N_CONST * 3;
+    double* row = p.part + ((size_t)frame * p.groups + group) * DSAC_N_CONST * 3;
     double X[K5_PTS], Y[K5_PTS], Z[K5_PTS], pu[K5_PTS], pv[K5_PTS], acc[K5_PTS][3];
 #pragma unroll
     for (int j = 0; j < K5_PTS; j++) {
@@ -456,7 +517,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_dscore(BwParams p) {
         acc[j][0] = acc[j][1] = acc[j][2] = 0;
     }
     const double f = p.f, cx = p.cx, cy = p.cy;
-    for (int h = 0; h < p.H; h++) {
+    for (int h = h_begin; h < h_end; h++) {
         __syncthreads();
         if (tid < 39) s_h[tid] = p.s.hypjp[((size_t)frame * p.H + h) * 39 + tid];
         __syncthreads();

@@ -80,6 +80,7 @@ struct dsac_engine {
     dsac_forward_out* pending_out = nullptr;   // results of a submitted, not yet awaited pass
     int pending_n = 0, pending_chunks = 0;
     BackwardScratch bw;
+    std::vector<std::pair<void*, size_t>> bw_pool;   // device buffers of dsac_backward_dsac, kept across calls
     cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // chunked H2D / compute / D2H pipeline of dsac_forward
     // tail split (dsac_set_tail_split): the whole sampler waves of a batch run on a high-priority side stream, the
     // frames of the last, partial wave on the caller's stream, so that scoring / refinement of the first part fill
@@ -166,6 +167,8 @@ void dsac_engine_destroy(dsac_engine* e) {
         if (p) cudaFree(p);
     if (e->h_stream_ncand) cudaFreeHost(e->h_stream_ncand);
     backward_scratch_free(&e->bw);
+    for (auto& slot : e->bw_pool)
+        if (slot.first) cudaFree(slot.first);
     delete e;
 }
 
@@ -261,6 +264,11 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         CUC(cudaMemcpy(e->d_perm, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
     CUC(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
+    // k_refine wants 8 CTAs x 26 KB of shared memory per SM: ask for the carve-out explicitly (the default heuristic
+    // need not pick the split the launch bounds were written for).  k_sample is left to the default: it spills to
+    // local memory and measured 5 % slower with the largest carve-out (3.39 vs 3.24 ms), i.e. with the smallest L1.
+    CUC(cudaFuncSetAttribute(k_refine, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    if (const char* co = getenv("DSAC_K1_CARVEOUT")) CUC(cudaFuncSetAttribute(k_sample, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
     {
         int per_sm = 0, sms = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample, K1_THREADS, sizeof(K1Smem));

@@ -71,10 +71,17 @@ constexpr int K1_WARPS = K1_THREADS / 32;
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 2
 #endif
-constexpr int K1_SUPER_MAX = 4096 / K1_THREADS;           // super-round = up to 4096 candidates (phase C packs them in 128 flag words)
+#ifndef K1_SUPER_CANDS
+#define K1_SUPER_CANDS 4096
+#endif
+static_assert(K1_SUPER_CANDS <= 4096, "phase C packs a super-round's flags in 128 words");
+constexpr int K1_SUPER_MAX = K1_SUPER_CANDS / K1_THREADS;  // super-round = up to K1_SUPER_CANDS candidates
 constexpr int K1_CANDS = K1_SUPER_MAX * K1_THREADS;       // candidates buffered per super-round
 constexpr int K1_WORDS = K1_CANDS * 8 + 1024;             // decoded stream words buffered per super-round
-constexpr int K1_WAVE = MT_N - MT_M;                      // 227 new MT19937 words per barrier
+#ifndef K1_GEN624
+#define K1_GEN624 1                                       // 1: a whole state regeneration (624 words) per barrier; 0: 227-word waves
+#endif
+constexpr int K1_WAVE = MT_N - MT_M;                      // 227 MT19937 words are mutually independent
 constexpr int K1_EV_CAP = 64;                             // repeated-pair events buffered per warp and super-round (expected: ~4)
 constexpr int K1_BRK_CAP = 160;                           // candidates with a repeated cell per super-round (expected: ~16)
 
@@ -88,7 +95,11 @@ struct __align__(8) CellRec {
 
 struct K1Smem {
     CellRec cell[DSAC_N_CONST];
+#if K1_GEN624
+    uint32_t st[2 * MT_N];                      // MT19937 state, double-buffered (old / new generation)
+#else
     uint32_t st[1024];                          // sliding window of the raw MT19937 sequence (linear index & 1023)
+#endif
     __align__(4) unsigned char vals[K1_WORDS];  // Lemire value (0..39) of stream word pos+i; 255 = rejected draw
     unsigned short cand_start[K1_CANDS + 512];    // word offset (from pos) where candidate i starts
     unsigned short q_idx[K1_CANDS];             // queue of candidates that need the full solve, ascending
@@ -232,8 +243,50 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
         long long want = (long long)S * K1_THREADS;
         if (cand_max - cand_base < want) want = cand_max - cand_base;
         const int n_target = (int)want;
+#if K1_GEN624
+        const int w_need = min(K1_WORDS - 640, n_target * 8 + 768);   // a regeneration may overshoot by 623 words
+#else
         const int w_need = min(K1_WORDS - 256, n_target * 8 + 768);   // a wave may overshoot by 226 words
+#endif
         // (leftover words [pos, gen) were moved to vals[0..gen-pos) at the end of the previous super-round)
+#if K1_GEN624
+        // One whole regeneration of the MT19937 state (624 words) per barrier.  In the in-place order k = 0..623 the word
+        //   new[k] = (k < 227 ? old[k+397] : new[k-227]) ^ twist(old[k], k < 623 ? old[k+1] : new[0])
+        // so thread t < 227 owns k = t, t+227, t+454: its second and third words need only its own previous result and
+        // OLD neighbours, which are read from the other half of the double-buffered state (k = 623 = 169+454 needs
+        // new[0], which thread 169 recomputes from old words).  No hazard inside the interval, 2.75x fewer barriers.
+        while ((int)(gen - pos) < w_need) {
+            const uint32_t* so = sm.st + ((gen / MT_N) & 1u) * MT_N;           // old state
+            uint32_t* sn = sm.st + (((gen / MT_N) & 1u) ^ 1u) * MT_N;            // new state
+            if (tid < K1_WAVE) {
+                uint32_t x[3];
+                x[0] = mt_twist(so[tid], so[tid + 1], so[tid + MT_M]);
+                x[1] = mt_twist(so[tid + K1_WAVE], so[tid + K1_WAVE + 1], x[0]);
+                const bool has3 = tid + 2 * K1_WAVE < MT_N;
+                if (has3) {
+                    const int k = tid + 2 * K1_WAVE;
+                    const uint32_t nxt = (k < MT_N - 1) ? so[k + 1] : mt_twist(so[0], so[1], so[MT_M]);
+                    x[2] = mt_twist(so[k], nxt, x[1]);
+                }
+#pragma unroll
+                for (int w = 0; w < 3; w++) {
+                    if (w < 2 || has3) {
+                        const int k = tid + w * K1_WAVE;
+                        sn[k] = x[w];
+                        const int off = (int)(gen - pos) + k;
+                        if (off >= 0 && off < K1_WORDS) {
+                            const uint64_t prod = (uint64_t)mt_temper(x[w]) * DSAC_GRID_CONST;
+                            const bool rej = (uint32_t)prod < ((0u - DSAC_GRID_CONST) % DSAC_GRID_CONST);  // Lemire: low < 2^32 mod 40
+                            sm.vals[off] = rej ? (unsigned char)255 : (unsigned char)(prod >> 32);
+                            if (rej) sm.any_reject = 1;
+                        }
+                    }
+                }
+            }
+            gen += MT_N;
+            __syncthreads();
+        }
+#else
         while ((int)(gen - pos) < w_need) {
             for (int el = tid; el < K1_WAVE; el += K1_THREADS) {
                 uint32_t n = gen + MT_N + el;  // linear index of the new element
@@ -250,6 +303,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
             gen += K1_WAVE;
             __syncthreads();
         }
+#endif
         const int w_avail = min((int)(gen - pos), K1_WORDS);
         K1_MARK(tA1);
 
@@ -574,7 +628,7 @@ struct ScoreParams {
 };
 
 constexpr int K2_THREADS = 320;  // 10 warps x 5 points per thread = 1600 scene coordinates
-constexpr int K2_PTS = 5;   // (the paired-reciprocal sigmoid sum in k_score is written out for exactly 5)
+constexpr int K2_PTS = 5;   // (the one-reciprocal sigmoid sum in k_score is written out for exactly 5)
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_MAX_TILE = 256;
 
@@ -664,9 +718,7 @@ __device__ void softargmax_tail(const ScoreParams& p, int frame, double* s_red /
 // caller then repeats the warp's tile with GUARDED = true, which overwrites everything the unguarded pass wrote.
 // Returns that flag.
 //
-// Soft inlier sigma(beta (tau - e)) = 1 / (1 + t), t = 2^(kbeta (e - tau)) <= 2^65 since e <= 100.  Two sigmoids share
-// one reciprocal, 1/w0 + 1/w1 = (w0 + w1) / (w0 w1): the product overflows only when both sigmoids are below 2^-63,
-// and then the quotient is (w0 + w1) * 0 = 0 -- no clamp needed.
+// Soft inlier sigma(beta (tau - e)) = 1 / (1 + t), t = 2^(kbeta (e - tau)); the thread's five sigmoids share one reciprocal.
 // One group of up to 8 hypotheses starting at hb.  FULL = all 8 exist: no per-hypothesis branch, so the eight bodies
 // form one basic block and the instruction scheduler can overlap the MUFU tail (rsqrt, ex2, rcp: 13 per hypothesis,
 // 8 issue cycles each on the XU pipe) of one hypothesis with the FMA-pipe projection of the next -- with a branch
@@ -702,23 +754,22 @@ __device__ __forceinline__ bool score_group8(const float* s_P, int hb, int nh, c
             }
             if (!GUARDED) rare |= (fminf(fminf(fminf(az[0], az[1]), fminf(az[2], az[3])), az[4]) == 0.f);
             float w[K2_PTS];
-#pragma unroll
-            for (int j = 0; j < K2_PTS; j++) {
-                if (WRITE_DM) __stcs(dm + (size_t)h * DSAC_N_CONST + tid + j * K2_THREADS, e[j]);
-                w[j] = 1.f + fast_ex2(fmaf(kbeta, e[j], -tau_k));
+            if (WRITE_DM) {   // cells 4 tid .. 4 tid + 3 as one 16-byte streaming store, cell 1280 + tid as a 4-byte one
+                float* row = dm + (size_t)h * DSAC_N_CONST;
+                __stcs(reinterpret_cast<float4*>(row) + tid, make_float4(e[0], e[1], e[2], e[3]));
+                __stcs(row + 4 * K2_THREADS + tid, e[4]);
             }
-#if defined(K2_SIGMOID5)
-            {   // (experiment) all five sigmoids over ONE reciprocal, t clamped to 2^25 so that the product stays below 2^126
-                float u0 = fminf(w[0], 33554433.f), u1 = fminf(w[1], 33554433.f), u2 = fminf(w[2], 33554433.f), u3 = fminf(w[3], 33554433.f), u4 = fminf(w[4], 33554433.f);
-                float p01 = u0 * u1, p23 = u2 * u3, qq = p23 * u4;
-                float Nn = fmaf(u0 + u1, qq, p01 * fmaf(u2 + u3, u4, p23));
+#pragma unroll
+            for (int j = 0; j < K2_PTS; j++) w[j] = 1.f + fast_ex2(fmaf(kbeta, e[j], -tau_k));
+            {   // all five sigmoids over ONE reciprocal, sum_j 1/w_j = N / D: w_j clamped to 2^25 + 1 so that D < 2^126
+                // (a sigmoid below 2^-25 is rounded up to 2^-25: <= 5e-6 absolute on a score, far inside tolerance); the
+                // XU / MIO queue is this kernel's scarcest resource, so one MUFU per five points beats one per two
+                const float u0 = fminf(w[0], 33554433.f), u1 = fminf(w[1], 33554433.f), u2 = fminf(w[2], 33554433.f),
+                            u3 = fminf(w[3], 33554433.f), u4 = fminf(w[4], 33554433.f);
+                const float p01 = u0 * u1, p23 = u2 * u3, qq = p23 * u4;
+                const float Nn = fmaf(u0 + u1, qq, p01 * fmaf(u2 + u3, u4, p23));
                 a = Nn * fast_rcp(p01 * qq);
             }
-#else
-            a = (w[0] + w[1]) * fast_rcp(w[0] * w[1]);
-            a = fmaf(w[2] + w[3], fast_rcp(w[2] * w[3]), a);
-            a += fast_rcp(w[4]);
-#endif
         }
         acc[u] = a;
     }
@@ -749,7 +800,7 @@ template <bool WRITE_DM, bool GUARDED>
 __device__ __forceinline__ bool score_tile(const float* s_P, int nh, const float (&X)[K2_PTS], const float (&Y)[K2_PTS],
                                            const float (&Z)[K2_PTS], const float (&pu)[K2_PTS], const float (&pv)[K2_PTS],
                                            float* dm, float kbeta, float tau_k, float* part, int tid, int lane) {
-    static_assert(K2_PTS == 5, "the sigmoid pairing is written out for 5 points per thread");
+    static_assert(K2_PTS == 5, "the shared-reciprocal sigmoid sum is written out for 5 points per thread");
     bool rare = false;
     int hb = 0;
     for (; hb + 8 <= nh; hb += 8) rare |= score_group8<WRITE_DM, GUARDED, true>(s_P, hb, nh, X, Y, Z, pu, pv, dm, kbeta, tau_k, part, tid, lane);
@@ -781,14 +832,14 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_BLOCKS) k_score(ScoreParams
     const int nh = min(p.tile, p.H - hbeg);
 
     if (!p.external_scores) {
-        // this thread's 5 scene coordinates and their (pixel - principal point), as floats
+        // this thread's 5 scene coordinates (cells 4 tid .. 4 tid + 3 and 1280 + tid) and their (pixel - principal point), as floats
         float X[K2_PTS], Y[K2_PTS], Z[K2_PTS], pu[K2_PTS], pv[K2_PTS];
         {
             const int16_t* c = p.coords + (size_t)frame * DSAC_N_CONST * 3;
             const int2* px = reinterpret_cast<const int2*>(p.pix + (size_t)frame * p.pix_stride);
 #pragma unroll
             for (int j = 0; j < K2_PTS; j++) {
-                int pt = tid + j * K2_THREADS;
+                const int pt = (j < 4) ? 4 * tid + j : 4 * K2_THREADS + tid;   // four adjacent cells + one: 16-byte stores of the error rows
                 X[j] = (float)__ldg(c + pt * 3);
                 Y[j] = (float)__ldg(c + pt * 3 + 1);
                 Z[j] = (float)__ldg(c + pt * 3 + 2);

@@ -733,10 +733,9 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         const double X3 = M0x + al * c1x + be * c2x + ga * c3x;
         const double Y3 = M0y + al * c1y + be * c2y + ga * c3y;
         const double Z3 = M0z + al * c1z + be * c2z + ga * c3z;
-        const double iz = 1.0 / Z3;
-        const double du = cx + f * X3 * iz - mu3, dv = cy + f * Y3 * iz - mv3;
-        const double e2 = du * du + dv * dv;
-        if (!(e2 > lim2)) return DSAC_FLAG(10);
+        // |(cx + f X3 / Z3 - mu3, cy + f Y3 / Z3 - mv3)|^2 > lim2, multiplied through by Z3^2 (no division)
+        const double gu = f * X3 - (mu3 - cx) * Z3, gv = f * Y3 - (mv3 - cy) * Z3, zz = Z3 * Z3;
+        if (!(gu * gu + gv * gv > lim2 * zz) || !(zz > 0)) return DSAC_FLAG(10);
     }
     return false;
 }

@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VAR = os.path.join(ROOT, "variants")
 # (name, extra nvcc flags)
-VARIANTS = [("cur", ""), ("k4_128x4", "-DK4_THREADS_DEF=128 -DK4_MIN_BLOCKS=4"), ("k2_sig5", "-DK2_SIGMOID5=1")]
+VARIANTS = [("cur", ""), ("k1_waves", "-DK1_GEN624=0"), ("k1_s3456", "-DK1_SUPER_CANDS=3456"), ("k1_s3456__co86", "-DK1_SUPER_CANDS=3456")]
 
 
 def build():
@@ -44,6 +44,8 @@ def run():
     with open(out, "a") as fh:
         for l in libs:
             env = dict(os.environ, DSAC_B200_LIB=os.path.join(VAR, l))
+            if "__co" in l:   # run-time option encoded in the variant name: preferred shared-memory carve-out of k_sample (percent)
+                env["DSAC_K1_CARVEOUT"] = l.split("__co")[1].split(".")[0]
             try:
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sweep_one.py")], env=env, capture_output=True, text=True, timeout=300)
                 lines = [x for x in r.stdout.splitlines() if x.startswith("SWEEP ")]

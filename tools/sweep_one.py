@@ -104,6 +104,23 @@ def main():
         run_pipe(4); torch.cuda.synchronize()
         t0 = time.perf_counter(); run_pipe(2 * STEPS); torch.cuda.synchronize()
         out["e2e_pipe_submitsplit%d_ms" % (mode == 2)] = (time.perf_counter() - t0) * 1e3 / (2 * STEPS)
+    # three engines in flight
+    eng_c = E.Engine(max_frames=NF)
+    o2 = host_result()
+    engs3, outs3 = (eng, eng_b, eng_c), (o0, o1, o2)
+    for e_ in engs3:
+        split(e_, 1)
+
+    def run_pipe3(k):
+        for i in range(k):
+            engs3[i % 3].forward_wait()
+            engs3[i % 3].forward_submit(h_c, h_p, h_g, frame0=0, out=outs3[i % 3])
+        for e_ in engs3:
+            e_.forward_wait()
+    run_pipe3(6); torch.cuda.synchronize()
+    t0 = time.perf_counter(); run_pipe3(3 * STEPS); torch.cuda.synchronize()
+    out["e2e_pipe3_ms"] = (time.perf_counter() - t0) * 1e3 / (3 * STEPS)
+    eng_c.close()
     eng_b.close()
 
     # ---- DSAC-variant round (refinement of all hypotheses + its backward: k_refine throughput)
