@@ -467,8 +467,8 @@ def main():
                            "copies its inputs from pinned host buffers (H2D) and reads poses/scores/errors back (D2H); the copies of one "
                            "step overlap the kernels of the other",
                     "pipeline_depth": 2,
-                    "note": "can exceed `value`: consecutive steps overlap on the GPU (the last wave of one step's sampler is filled by "
-                            "the next step's kernels), which the per-step-isolated, L2-flushed `value` measurement forbids",
+                    "note": "can exceed `value`: consecutive steps overlap on the GPU (the last, partial wave of one step's sampler is "
+                            "filled by the other engine's kernels), which the per-step-isolated, L2-flushed `value` measurement forbids",
                     "sync_call": {"value": e2e_sync_value, "ms_per_step": 1e3 * float(t[1].item()) / args.steps,
                                   "api": "one blocking dsac_forward per step (H2D, kernels, D2H strictly serial)"}},
             "gpu_launches": gpu_launches,

@@ -159,6 +159,40 @@ __device__ __forceinline__ int cand_parse_fast(const unsigned char* vals, int q,
     return cand_parse(vals, q, limit, cells);
 }
 
+// Length in (x, y) pairs of the candidate that starts at pair sp, for a window without rejected draws (every word is a
+// value, so candidates are sequences of pairs): pairs are taken until 4 distinct ones are found.  The first 8 pairs are
+// fetched with independent loads (a candidate longer than that needs >= 4 repeats); returns -1 if the window ends first.
+__device__ __forceinline__ int cand_pairs_len(const unsigned short* pr16, int sp, int limit) {
+    if (sp + 8 <= limit) {
+        unsigned v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = pr16[sp + i];
+        unsigned c0 = v[0], c1 = 0x10000u, c2 = 0x10000u;   // 0x10000: no 16-bit pair value
+        int n = 1;
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            const bool dup = (v[i] == c0) | (v[i] == c1) | (v[i] == c2);
+            if (!dup) {
+                if (n == 3) return i + 1;
+                if (n == 1) c1 = v[i]; else c2 = v[i];
+                n++;
+            }
+        }
+    }
+    unsigned c[4];
+    int n = 0, q = sp;
+    while (n < 4) {
+        if (q >= limit) return -1;
+        const unsigned v = pr16[q++];
+        bool dup = false;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            if (j < n && c[j] == v) dup = true;
+        if (!dup) { c[n < 3 ? n : 3] = v; n++; }
+    }
+    return q - sp;
+}
+
 // One CTA per (frame, stream).  Per super-round of up to S x 256 candidates:
 //   A  MT19937 in waves of 227 words (one barrier each), every word decoded on the fly to its
 //      uniform_int_distribution value; candidate boundaries by a block-wide fixed point over per-thread runs
@@ -325,13 +359,16 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
             int cnt = 0;
             for (int k0 = wbeg; k0 < wend; k0 += 32) {
                 const int k = k0 + lane;
-                unsigned d = 0;
-                if (k < wend) {
-                    const unsigned pk = pr16[k];
-                    const unsigned p1 = (k >= 1) ? pr16[k - 1] : 0xffffu, p2 = (k >= 2) ? pr16[k - 2] : 0xffffu,
-                                   p3 = (k >= 3) ? pr16[k - 3] : 0xffffu;
-                    d = (pk == p1) ? 1u : (pk == p2) ? 2u : (pk == p3) ? 3u : 0u;
+                // pair k against its three predecessors: neighbours' values by shuffle, lanes 0..2 fetch theirs
+                const unsigned pk = (k < scan_end) ? pr16[k] : 0xffffu;
+                unsigned p1 = __shfl_up_sync(0xffffffffu, pk, 1), p2 = __shfl_up_sync(0xffffffffu, pk, 2), p3 = __shfl_up_sync(0xffffffffu, pk, 3);
+                if (lane < 3) {
+                    if (lane < 1) p1 = (k >= 1) ? pr16[k - 1] : 0xffffu;
+                    if (lane < 2) p2 = (k >= 2) ? pr16[k - 2] : 0xffffu;
+                    p3 = (k >= 3) ? pr16[k - 3] : 0xffffu;
                 }
+                unsigned d = 0;
+                if (k < wend) d = (pk == p1) ? 1u : (pk == p2) ? 2u : (pk == p3) ? 3u : 0u;
                 const unsigned m = __ballot_sync(0xffffffffu, d != 0);
                 if (d) {
                     const int slot = cnt + __popc(m & ((1u << lane) - 1u));
@@ -355,12 +392,11 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
                         const int j = (k - cur) >> 2, sp = cur + 4 * j;
                         if (k - d < sp) continue;              // the equal pair belongs to the previous candidate
                         if (ci + j >= n_target) { stop_at = n_target; break; }
-                        int cells[4];
-                        const int q = cand_parse(sm.vals, 2 * sp, 2 * scan_end, cells);
-                        if (q < 0) { stop_at = ci + j; break; }   // window ends inside this candidate
-                        if ((q & 1) || nb >= K1_BRK_CAP) { fail = true; break; }
+                        const int np = cand_pairs_len(pr16, sp, scan_end);
+                        if (np < 0) { stop_at = ci + j; break; }   // window ends inside this candidate
+                        if (nb >= K1_BRK_CAP) { fail = true; break; }
                         ci += j + 1;
-                        cur = q >> 1;
+                        cur = sp + np;
                         sm.brk_ci[nb] = (unsigned short)ci;
                         sm.brk_cur[nb] = (unsigned short)cur;
                         nb++;

@@ -1,11 +1,17 @@
+# Final capture of a round (one gpurun call): GPU tests, bench line, ncu launch list of the bench, full ncu captures of
+# the forward kernels and of the upstream gather, compute-sanitizer.  Tag = $1 (default r01).
 set -x
+T=${1:-r01}
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r01b_pytest.log 2>&1; tail -2 gpurun_out/r01b_pytest.log
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r01b_bench_line.json 2> gpurun_out/r01b_bench.err; tail -c 600 gpurun_out/r01b_bench_line.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01b.csv python bench.py --steps 2 --warmup 3 > gpurun_out/r01b_ncu_bench.log 2>&1
-for k in k_score k_sample k_refine; do timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -s 2 -f -o gpurun_out/${k}_r01b python tools/prof_driver.py > gpurun_out/ncu_$k.log 2>&1; done
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gather -c 1 -s 2 -f -o gpurun_out/k_gather_r01b python tools/gather_probe.py > gpurun_out/ncu_k_gather.log 2>&1
-for tool in memcheck racecheck initcheck; do NB=5 REPS=1 timeout 500 compute-sanitizer --tool $tool python tools/prof_driver.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY" | sed "s/^/$tool fwd: /"; done > gpurun_out/sanitizer_r01b.txt 2>&1
-timeout 500 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_backward.py -m gpu -q -k "dsac_variant_backward_matches_oracle and 16" 2>&1 | grep -E "ERROR SUMMARY|passed|failed" | sed "s/^/memcheck backward_dsac: /" >> gpurun_out/sanitizer_r01b.txt
-cat gpurun_out/sanitizer_r01b.txt
-ls -la gpurun_out | tail -12
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv,noheader; nproc
+timeout 600 python -m pytest tests -m gpu -q --timeout=300 -rf > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_line.json 2> gpurun_out/${T}_bench.err; tail -c 400 gpurun_out/${T}_bench_line.json; tail -3 gpurun_out/${T}_bench.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err; tail -c 300 gpurun_out/${T}_bench_reference.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${T}.csv python bench.py --steps 2 --warmup 3 > gpurun_out/${T}_ncu_bench.log 2>&1
+for k in k_score k_sample k_refine; do DSAC_TAIL_SPLIT=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -s 2 -f -o gpurun_out/${k}_${T} python tools/prof_driver.py > gpurun_out/ncu_$k.log 2>&1; done
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gather -c 1 -s 2 -f -o gpurun_out/k_gather_${T} python tools/gather_probe.py > gpurun_out/ncu_k_gather.log 2>&1
+for tool in memcheck racecheck initcheck; do NB=5 REPS=1 timeout 400 compute-sanitizer --tool $tool python tools/prof_driver.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY" | sed "s/^/$tool fwd (5 frames): /"; done > gpurun_out/sanitizer_${T}.txt 2>&1
+timeout 400 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_backward.py -m gpu -q -k "test_backward_matches_oracle or (dsac_variant_backward_matches_oracle and 16)" 2>&1 | grep -E "ERROR SUMMARY|passed|failed" | sed "s/^/memcheck backward + backward_dsac: /" >> gpurun_out/sanitizer_${T}.txt
+cat gpurun_out/sanitizer_${T}.txt
+ls -la gpurun_out | tail -15

@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VAR = os.path.join(ROOT, "variants")
 # (name, extra nvcc flags)
-VARIANTS = [("cur", ""), ("k1_waves", "-DK1_GEN624=0"), ("k1_s3456", "-DK1_SUPER_CANDS=3456"), ("k1_s3456__co86", "-DK1_SUPER_CANDS=3456")]
+VARIANTS = [("cur", "")]
 
 
 def build():
