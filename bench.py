@@ -180,6 +180,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not mix with the ONE JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
