@@ -327,6 +327,16 @@ def main():
         except Exception:
             traffic = None
     ssum = sum(stage_ms.values())
+
+    def ncu_value(fname, key):
+        """A metric of the committed ncu summary of this round's kernel (profiles/, static evidence; None if absent)."""
+        try:
+            for line in open(os.path.join(ROOT, "profiles", fname)):
+                if line.strip().startswith(key + " "):
+                    return float(line.split()[1])
+        except Exception:
+            pass
+        return None
     roofline = {"kernel": "k_score<write_diffmaps=1> (HxN reprojection-error matrix + soft-inlier score + soft-argmax tail)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_M * nf,
@@ -479,7 +489,12 @@ def main():
                                   "see profiles/r01_k_sample_full.txt)" % (100 * stage_ms["k_sample"] / ssum),
                         "candidates_per_s": quality["candidates_per_frame"] * nf / (stage_ms["k_sample"] * 1e-3),
                         "candidates_per_accepted_hypothesis": quality["candidates_per_frame"] / H,
-                        "ms_per_launch": stage_ms["k_sample"]},
+                        "ms_per_launch": stage_ms["k_sample"],
+                        "ncu": {"source": "profiles/r01_k_sample_full.txt (one launch under ncu --set full)",
+                                "fp64_pipe_pct": ncu_value("r01_k_sample_full.txt", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                                "issue_active_pct": ncu_value("r01_k_sample_full.txt", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                "barrier_stalls_per_issue": ncu_value("r01_k_sample_full.txt", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
+                                "dram_pct": ncu_value("r01_k_sample_full.txt", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}},
             "cpu_baseline": cpu,
             "single_frame": single,
             "train_round": train,
