@@ -668,22 +668,6 @@ constexpr int K2_PTS = 5;   // (the one-reciprocal sigmoid sum in k_score is wri
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_MAX_TILE = 256;
 
-__device__ __forceinline__ float fast_rcp(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_rsqrt(float x) {
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_ex2(float x) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
 // softmax / entropy / soft-argmax over the H hypotheses of one frame, in double
 // (softMax cnn_softam.h:535-553, entropy :80-88, averaging :1082-1094).
 __device__ void softargmax_tail(const ScoreParams& p, int frame, double* s_red /* >= 8*K2_WARPS doubles */) {
@@ -775,37 +759,16 @@ __device__ __forceinline__ bool score_group8(const float* s_P, int hb, int nh, c
             const float4 r2 = *reinterpret_cast<const float4*>(s_P + h * 12 + 8);
             float e[K2_PTS], az[K2_PTS];
 #pragma unroll
-            for (int j = 0; j < K2_PTS; j++) {
-                const float xs = fmaf(r0.x, X[j], fmaf(r0.y, Y[j], fmaf(r0.z, Z[j], r0.w)));
-                const float ys = fmaf(r1.x, X[j], fmaf(r1.y, Y[j], fmaf(r1.z, Z[j], r1.w)));
-                float zs = fmaf(r2.x, X[j], fmaf(r2.y, Y[j], fmaf(r2.z, Z[j], r2.w)));
-                az[j] = fabsf(zs);
-                if (GUARDED) zs = (zs != 0.f) ? zs : 1.f;  // z ? 1/z : 1 (cv::projectPoints)
-                const float du = fmaf(pu[j], zs, -xs);
-                const float dv = fmaf(pv[j], zs, -ys);
-                const float A = fmaf(du, du, dv * dv);
-                // A = 0 (the float projection lands exactly on the pixel -- it does happen for the three points a P3P pose
-                // fits exactly): 0 * rsqrt(floor) = 0.  A > 0 implies A >= ulp^2 and z != 0 implies z^2 far above the floor.
-                e[j] = fminf(A * fast_rsqrt(fmaxf(A * (zs * zs), 1e-30f)), DSAC_MAXINPUT_F);  // min(norm, CNN_OBJ_MAXINPUT), cnn_softam.h:357
-            }
+            for (int j = 0; j < K2_PTS; j++)
+                e[j] = score_pair_error<GUARDED>(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, X[j], Y[j], Z[j],
+                                                 pu[j], pv[j], &az[j]);
             if (!GUARDED) rare |= (fminf(fminf(fminf(az[0], az[1]), fminf(az[2], az[3])), az[4]) == 0.f);
-            float w[K2_PTS];
             if (WRITE_DM) {   // cells 4 tid .. 4 tid + 3 as one 16-byte streaming store, cell 1280 + tid as a 4-byte one
                 float* row = dm + (size_t)h * DSAC_N_CONST;
                 __stcs(reinterpret_cast<float4*>(row) + tid, make_float4(e[0], e[1], e[2], e[3]));
                 __stcs(row + 4 * K2_THREADS + tid, e[4]);
             }
-#pragma unroll
-            for (int j = 0; j < K2_PTS; j++) w[j] = 1.f + fast_ex2(fmaf(kbeta, e[j], -tau_k));
-            {   // all five sigmoids over ONE reciprocal, sum_j 1/w_j = N / D: w_j clamped to 2^25 + 1 so that D < 2^126
-                // (a sigmoid below 2^-25 is rounded up to 2^-25: <= 5e-6 absolute on a score, far inside tolerance); the
-                // XU / MIO queue is this kernel's scarcest resource, so one MUFU per five points beats one per two
-                const float u0 = fminf(w[0], 33554433.f), u1 = fminf(w[1], 33554433.f), u2 = fminf(w[2], 33554433.f),
-                            u3 = fminf(w[3], 33554433.f), u4 = fminf(w[4], 33554433.f);
-                const float p01 = u0 * u1, p23 = u2 * u3, qq = p23 * u4;
-                const float Nn = fmaf(u0 + u1, qq, p01 * fmaf(u2 + u3, u4, p23));
-                a = Nn * fast_rcp(p01 * qq);
-            }
+            a = score_sigmoid_sum5(e, kbeta, tau_k);
         }
         acc[u] = a;
     }

@@ -165,6 +165,53 @@ DSAC_HD int reproj_below_thr_fast(const float* P, float X, float Y, float Z, flo
     return -1;
 }
 
+// ----------------------------------------------------------------------------- k_score's fp32 arithmetic
+// MUFU approximations on the device, plain libm on the host (the host build only serves the CPU-side checks)
+#if defined(__CUDA_ARCH__)
+DSAC_HD float approx_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DSAC_HD float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DSAC_HD float approx_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+DSAC_HD float approx_rsqrt(float x) { return 1.0f / sqrtf(x); }
+DSAC_HD float approx_rcp(float x) { return 1.0f / x; }
+DSAC_HD float approx_ex2(float x) { return exp2f(x); }
+#endif
+
+// One entry of the H x N reprojection-error matrix as k_score computes it: rows r0 = (f R0 | f t0), r1 = (f R1 | f t1),
+// r2 = (R2 | t2) of the hypothesis in float, scene coordinate (X, Y, Z), pixel minus principal point (pu, pv).
+//   e = |pix - proj| = sqrt(A) / |z|,  A = (pu z - xs)^2 + (pv z - ys)^2   ->   e = A * rsqrt(max(A z^2, floor)),
+// clamped at 100 (CNN_OBJ_MAXINPUT, cnn_softam.h:357).  A = 0 (the float projection lands exactly on the pixel -- it does
+// happen for the three points a P3P pose fits exactly) gives 0 * rsqrt(floor) = 0; A > 0 implies A >= ulp^2 and z != 0
+// implies z^2 far above the floor.  GUARDED adds cv::projectPoints' z ? 1/z : 1; *az returns |z| before that substitution
+// (the unguarded caller uses it to detect z == 0 and repeat with GUARDED).
+template <bool GUARDED>
+DSAC_HD float score_pair_error(float r0x, float r0y, float r0z, float r0w, float r1x, float r1y, float r1z, float r1w, float r2x,
+                               float r2y, float r2z, float r2w, float X, float Y, float Z, float pu, float pv, float* az) {
+    const float xs = fmaf(r0x, X, fmaf(r0y, Y, fmaf(r0z, Z, r0w)));
+    const float ys = fmaf(r1x, X, fmaf(r1y, Y, fmaf(r1z, Z, r1w)));
+    float zs = fmaf(r2x, X, fmaf(r2y, Y, fmaf(r2z, Z, r2w)));
+    *az = fabsf(zs);
+    if (GUARDED) zs = (zs != 0.f) ? zs : 1.f;  // z ? 1/z : 1 (cv::projectPoints)
+    const float du = fmaf(pu, zs, -xs);
+    const float dv = fmaf(pv, zs, -ys);
+    const float A = fmaf(du, du, dv * dv);
+    return fminf(A * approx_rsqrt(fmaxf(A * (zs * zs), 1e-30f)), DSAC_MAXINPUT_F);
+}
+
+// Sum of the soft-inlier sigmoids sigma(beta (tau - e_j)) = 1 / (1 + 2^(kbeta e_j - tau_k)) of five errors over ONE
+// reciprocal, sum_j 1/w_j = N / D: w_j clamped to 2^25 + 1 so that D < 2^126 (a sigmoid below 2^-25 is rounded up to
+// 2^-25: <= 5e-6 absolute on a score).  The XU / MIO queue is k_score's scarcest resource, so one MUFU per five points
+// beats one per two.
+DSAC_HD float score_sigmoid_sum5(const float e[5], float kbeta, float tau_k) {
+    float w[5];
+    for (int j = 0; j < 5; j++) w[j] = 1.f + approx_ex2(fmaf(kbeta, e[j], -tau_k));
+    const float u0 = fminf(w[0], 33554433.f), u1 = fminf(w[1], 33554433.f), u2 = fminf(w[2], 33554433.f),
+                u3 = fminf(w[3], 33554433.f), u4 = fminf(w[4], 33554433.f);
+    const float p01 = u0 * u1, p23 = u2 * u3, qq = p23 * u4;
+    const float Nn = fmaf(u0 + u1, qq, p01 * fmaf(u2 + u3, u4, p23));
+    return Nn * approx_rcp(p01 * qq);
+}
+
 // ----------------------------------------------------------------------------- P3P
 // Largest real root of y^3 + a2 y^2 + a1 y + a0 (the resolvent cubic of Ferrari's method).
 #if defined(__CUDA_ARCH__)

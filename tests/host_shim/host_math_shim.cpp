@@ -182,3 +182,43 @@ int shim_lm_refine(int n, const float* obj, const float* img, double f, double c
     return lm.iters;
 }
 }
+
+// ---- k_score's fp32 arithmetic (score_pair_error / score_sigmoid_sum5) on the host: one hypothesis against n cells.
+// err_f32 / err_exact [n]: the fp32 entry (guarded as the kernel ends up computing it: unguarded unless z == 0) and
+// getDiffMap's exact entry; *score = alpha * sum of the soft-inlier sigmoids in k_score's order of 5 cells per thread
+// (cells 4t..4t+3 and 1280+t), *score_exact the same sum in double from the exact entries.  n must be 1600.
+extern "C" void shim_score_hypothesis(const double* rvec, const double* tvec, const int16_t* coords, const int32_t* pix, double f,
+                                      double cx, double cy, double thr, double alpha, double beta, float* err_f32, float* err_exact,
+                                      double* score, double* score_exact) {
+    const int N = 1600, T = 320;
+    double R[9];
+    dsac::rodrigues_v2m(rvec, R);
+    float P[12];
+    for (int row = 0; row < 3; row++)
+        for (int col = 0; col < 4; col++) {
+            double v = col < 3 ? R[row * 3 + col] : tvec[row];
+            P[row * 4 + col] = (float)(row < 2 ? f * v : v);
+        }
+    const float kbeta = (float)(beta * 1.4426950408889634), tau_k = (float)thr * kbeta, cxf = (float)cx, cyf = (float)cy;
+    double se = 0;
+    float ssum = 0.f;   // (the kernel reduces per-thread sums over warps in a fixed tree; a float running sum is close enough here)
+    for (int t = 0; t < T; t++) {
+        float e[5];
+        for (int j = 0; j < 5; j++) {
+            const int c = j < 4 ? 4 * t + j : 4 * T + t;
+            const float X = coords[c * 3], Y = coords[c * 3 + 1], Z = coords[c * 3 + 2];
+            const float pu = (float)pix[c * 2] - cxf, pv = (float)pix[c * 2 + 1] - cyf;
+            float az;
+            e[j] = dsac::score_pair_error<false>(P[0], P[1], P[2], P[3], P[4], P[5], P[6], P[7], P[8], P[9], P[10], P[11], X, Y, Z, pu, pv, &az);
+            if (az == 0.f)
+                e[j] = dsac::score_pair_error<true>(P[0], P[1], P[2], P[3], P[4], P[5], P[6], P[7], P[8], P[9], P[10], P[11], X, Y, Z, pu, pv, &az);
+            err_f32[c] = e[j];
+            err_exact[c] = dsac::reproj_error_exact(R, tvec, X, Y, Z, f, cx, cy, (float)pix[c * 2], (float)pix[c * 2 + 1]);
+            se += 1.0 / (1.0 + exp(-beta * (thr - (double)err_exact[c])));
+        }
+        ssum += dsac::score_sigmoid_sum5(e, kbeta, tau_k);
+    }
+    (void)N;
+    *score = alpha * (double)ssum;
+    *score_exact = alpha * se;
+}

@@ -224,3 +224,50 @@ def test_lm_loop_of_the_refinement_matches_oracle(oracle, host_shim):
     # reaches 1.5e-10 rad / 7e-8 mm with either factorisation
     assert np.percentile(dr, 90) <= 1e-14 and np.percentile(dt, 90) <= 1e-11
     assert max(dr) <= 1e-9 and max(dt) <= 1e-6
+
+
+def test_score_kernel_arithmetic_matches_the_exact_error_matrix(host_shim, engine_mod):
+    """k_score's fp32 formulation (score_pair_error: one rsqrt with a floor, no per-pair guards; score_sigmoid_sum5: five
+    sigmoids over one reciprocal), compiled for the host, against getDiffMap's exact arithmetic (cnn_softam.h:319-362)
+    and the double-precision soft-inlier score: entries within the 2e-3 px contract, scores within 1e-5 relative + 5e-6."""
+    E = engine_mod
+    rng = np.random.default_rng(12)
+    coords, pix, gt_cv, _ = E.synth_frames(6)
+
+    def run(rv, tv, cc, pp):
+        e32, ex = np.zeros(1600, np.float32), np.zeros(1600, np.float32)
+        s, sx = C.c_double(0), C.c_double(0)
+        cc = np.ascontiguousarray(cc, np.int16); pp = np.ascontiguousarray(pp, np.int32)
+        rv = np.ascontiguousarray(rv, np.float64); tv = np.ascontiguousarray(tv, np.float64)
+        host_shim.shim_score_hypothesis(rv.ctypes.data_as(C.c_void_p), tv.ctypes.data_as(C.c_void_p), cc.ctypes.data_as(C.c_void_p),
+                                        pp.ctypes.data_as(C.c_void_p), C.c_double(525), C.c_double(320), C.c_double(240), C.c_double(10),
+                                        C.c_double(0.1), C.c_double(0.5), e32.ctypes.data_as(C.c_void_p), ex.ctypes.data_as(C.c_void_p),
+                                        C.byref(s), C.byref(sx))
+        return e32, ex, s.value, sx.value
+
+    worst = 0.0
+    for f in range(6):
+        for k in range(30):
+            sc = 0.0 if k == 0 else 10.0 ** rng.uniform(-5, -0.5)
+            rv = gt_cv[f, :3] + rng.normal(0, sc, 3)
+            tv = gt_cv[f, 3:] + rng.normal(0, 1000 * sc, 3)
+            e32, ex, s, sx = run(rv, tv, coords[f], pix[f])
+            worst = max(worst, np.abs(e32 - ex).max())
+            assert np.abs(e32 - ex).max() <= 2e-3
+            assert abs(s - sx) <= 1e-5 * sx + 5e-6
+    assert worst > 0        # (the two arithmetics do differ: fp32 vs double with float rounding of the projection)
+    # value-encoded zero pose (R = I, t = 0): cells with Z = 0 lie in the camera plane (1/z := 1), cells at the origin
+    # project onto the principal point; saturated coordinates must stay finite
+    cz = coords[0].copy()
+    cz[::3] = 0
+    cz[1::11, 2] = 0
+    cz[5::13] = 32767
+    cz[7::17] = -32768
+    e32, ex, s, sx = run(np.zeros(3), np.zeros(3), cz, pix[0])
+    assert np.isfinite(e32).all() and np.abs(e32 - ex).max() <= 2e-3 and (e32[::3] < 100).any()
+    assert abs(s - sx) <= 1e-5 * sx + 5e-6
+    # a pose fitted exactly through a cell gives A = 0 there: the floor under the rsqrt must return exactly 0
+    c1 = coords[0].copy(); p1 = pix[0].copy()
+    c1[0] = (0, 0, 1000); p1[0] = (320, 240)
+    e32, ex, _, _ = run(np.zeros(3), np.zeros(3), c1, p1)
+    assert e32[0] == 0.0 and ex[0] == 0.0
