@@ -284,24 +284,15 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
 #endif
         // (leftover words [pos, gen) were moved to vals[0..gen-pos) at the end of the previous super-round)
 #if K1_GEN624
-        // One whole regeneration of the MT19937 state (624 words) per barrier.  In the in-place order k = 0..623 the word
-        //   new[k] = (k < 227 ? old[k+397] : new[k-227]) ^ twist(old[k], k < 623 ? old[k+1] : new[0])
-        // so thread t < 227 owns k = t, t+227, t+454: its second and third words need only its own previous result and
-        // OLD neighbours, which are read from the other half of the double-buffered state (k = 623 = 169+454 needs
-        // new[0], which thread 169 recomputes from old words).  No hazard inside the interval, 2.75x fewer barriers.
+        // One whole regeneration of the MT19937 state (624 words) per barrier (mt_regenerate_words, sampler.cuh): thread
+        // t < 227 produces the words t, t+227, t+454 from its own previous result and OLD neighbours, which are read from the
+        // other half of the double-buffered state.  No hazard inside the interval, 2.75x fewer barriers than 227-word waves.
         while ((int)(gen - pos) < w_need) {
             const uint32_t* so = sm.st + ((gen / MT_N) & 1u) * MT_N;           // old state
             uint32_t* sn = sm.st + (((gen / MT_N) & 1u) ^ 1u) * MT_N;            // new state
             if (tid < K1_WAVE) {
                 uint32_t x[3];
-                x[0] = mt_twist(so[tid], so[tid + 1], so[tid + MT_M]);
-                x[1] = mt_twist(so[tid + K1_WAVE], so[tid + K1_WAVE + 1], x[0]);
-                const bool has3 = tid + 2 * K1_WAVE < MT_N;
-                if (has3) {
-                    const int k = tid + 2 * K1_WAVE;
-                    const uint32_t nxt = (k < MT_N - 1) ? so[k + 1] : mt_twist(so[0], so[1], so[MT_M]);
-                    x[2] = mt_twist(so[k], nxt, x[1]);
-                }
+                const bool has3 = mt_regenerate_words(so, tid, x) == 3;
 #pragma unroll
                 for (int w = 0; w < 3; w++) {
                     if (w < 2 || has3) {

@@ -46,6 +46,21 @@ DSAC_HD void mt_twist_all_seq(uint32_t* mt) {
     mt[MT_N - 1] = mt_twist(mt[MT_N - 1], mt[0], mt[MT_M - 1]);
 }
 
+// Block-parallel regeneration of the whole state (k_sample): in the in-place order k = 0..623 the word
+//   new[k] = (k < 227 ? old[k+397] : new[k-227]) ^ twist(old[k], k < 623 ? old[k+1] : new[0])
+// so thread t < 227 owns k = t, t+227, t+454 (the last only for t < 170): its second and third word need its own previous
+// result and OLD neighbours only (k = 623 = 169+454 needs new[0], recomputed here from old words).  Returns the number of
+// words produced (x[w] is new[t + 227 w]); `so` is the old state, which the caller keeps apart from the new one.
+DSAC_HD int mt_regenerate_words(const uint32_t* so, int t, uint32_t x[3]) {
+    x[0] = mt_twist(so[t], so[t + 1], so[t + MT_M]);
+    x[1] = mt_twist(so[t + (MT_N - MT_M)], so[t + (MT_N - MT_M) + 1], x[0]);
+    const int k = t + 2 * (MT_N - MT_M);
+    if (k >= MT_N) return 2;
+    const uint32_t nxt = (k < MT_N - 1) ? so[k + 1] : mt_twist(so[0], so[1], so[MT_M]);
+    x[2] = mt_twist(so[k], nxt, x[1]);
+    return 3;
+}
+
 // A window of tempered stream words addressed by absolute stream position.
 struct WordRing {
     const uint32_t* buf;

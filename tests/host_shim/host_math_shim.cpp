@@ -222,3 +222,20 @@ extern "C" void shim_score_hypothesis(const double* rvec, const double* tvec, co
     *score = alpha * (double)ssum;
     *score_exact = alpha * se;
 }
+
+// k_sample's block-parallel MT19937 regeneration (mt_regenerate_words), the 227 threads run one after the other on a
+// double-buffered state exactly as the kernel holds it: n_blocks x 624 tempered outputs.
+extern "C" void shim_mt_regenerated(uint32_t seed, int n_blocks, uint32_t* out) {
+    uint32_t st[2 * dsac::MT_N];
+    dsac::mt_seed(st, seed);
+    for (int r = 0; r < n_blocks; r++) {
+        const uint32_t* so = st + (r & 1) * dsac::MT_N;
+        uint32_t* sn = st + ((r & 1) ^ 1) * dsac::MT_N;
+        for (int t = dsac::MT_N - dsac::MT_M - 1; t >= 0; t--) {   // any thread order: threads only read the old state
+            uint32_t x[3];
+            const int nw = dsac::mt_regenerate_words(so, t, x);
+            for (int w = 0; w < nw; w++) sn[t + w * (dsac::MT_N - dsac::MT_M)] = x[w];
+        }
+        for (int k = 0; k < dsac::MT_N; k++) out[r * dsac::MT_N + k] = dsac::mt_temper(sn[k]);
+    }
+}

@@ -61,6 +61,15 @@ def test_device_mt19937_matches_std(oracle, host_shim):
     assert np.array_equal(out, oracle.mt19937_raw(1305, 2000))
 
 
+def test_block_parallel_mt19937_regeneration_matches_std(oracle, host_shim):
+    """k_sample regenerates the whole 624-word state per barrier, thread t < 227 producing the words t, t+227, t+454 from
+    old neighbours and its own results (mt_regenerate_words): same stream as std::mt19937, in any thread order."""
+    for seed in (1305, 1306, 5489, 0xffffffff):
+        out = np.zeros(5 * 624, np.uint32)
+        host_shim.shim_mt_regenerated(C.c_uint32(seed), 5, oracle._p(out))
+        assert np.array_equal(out, oracle.mt19937_raw(seed, 5 * 624))
+
+
 def test_stream_chunk_partition(host_shim):
     for H, T in ((256, 1), (256, 8), (10, 3), (7, 7), (64, 5)):
         covered = []
