@@ -159,40 +159,6 @@ __device__ __forceinline__ int cand_parse_fast(const unsigned char* vals, int q,
     return cand_parse(vals, q, limit, cells);
 }
 
-// Length in (x, y) pairs of the candidate that starts at pair sp, for a window without rejected draws (every word is a
-// value, so candidates are sequences of pairs): pairs are taken until 4 distinct ones are found.  The first 8 pairs are
-// fetched with independent loads (a candidate longer than that needs >= 4 repeats); returns -1 if the window ends first.
-__device__ __forceinline__ int cand_pairs_len(const unsigned short* pr16, int sp, int limit) {
-    if (sp + 8 <= limit) {
-        unsigned v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = pr16[sp + i];
-        unsigned c0 = v[0], c1 = 0x10000u, c2 = 0x10000u;   // 0x10000: no 16-bit pair value
-        int n = 1;
-#pragma unroll
-        for (int i = 1; i < 8; i++) {
-            const bool dup = (v[i] == c0) | (v[i] == c1) | (v[i] == c2);
-            if (!dup) {
-                if (n == 3) return i + 1;
-                if (n == 1) c1 = v[i]; else c2 = v[i];
-                n++;
-            }
-        }
-    }
-    unsigned c[4];
-    int n = 0, q = sp;
-    while (n < 4) {
-        if (q >= limit) return -1;
-        const unsigned v = pr16[q++];
-        bool dup = false;
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            if (j < n && c[j] == v) dup = true;
-        if (!dup) { c[n < 3 ? n : 3] = v; n++; }
-    }
-    return q - sp;
-}
-
 // One CTA per (frame, stream).  Per super-round of up to S x 256 candidates:
 //   A  MT19937 in waves of 227 words (one barrier each), every word decoded on the fly to its
 //      uniform_int_distribution value; candidate boundaries by a block-wide fixed point over per-thread runs

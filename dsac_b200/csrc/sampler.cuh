@@ -104,6 +104,40 @@ DSAC_HD uint32_t parse_candidate(const WordRing& ring, uint32_t start, uint32_t 
     return pos - start;
 }
 
+// Length in (x, y) pairs of the candidate that starts at pair sp, for a window without rejected draws (every word is a
+// value, so candidates are sequences of pairs): pairs are taken until 4 distinct ones are found.  The first 8 pairs are
+// fetched with independent loads (a candidate longer than that needs >= 4 repeats); returns -1 if the window ends first.
+DSAC_HD int cand_pairs_len(const unsigned short* pr16, int sp, int limit) {
+    if (sp + 8 <= limit) {
+        unsigned v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = pr16[sp + i];
+        unsigned c0 = v[0], c1 = 0x10000u, c2 = 0x10000u;   // 0x10000: no 16-bit pair value
+        int n = 1;
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            const bool dup = (v[i] == c0) | (v[i] == c1) | (v[i] == c2);
+            if (!dup) {
+                if (n == 3) return i + 1;
+                if (n == 1) c1 = v[i]; else c2 = v[i];
+                n++;
+            }
+        }
+    }
+    unsigned c[4];
+    int n = 0, q = sp;
+    while (n < 4) {
+        if (q >= limit) return -1;
+        const unsigned v = pr16[q++];
+        bool dup = false;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            if (j < n && c[j] == v) dup = true;
+        if (!dup) { c[n < 3 ? n : 3] = v; n++; }
+    }
+    return q - sp;
+}
+
 // libgomp static schedule of `#pragma omp parallel for` over h (cnn_softam.h:1010):
 // stream s of T owns a contiguous chunk; the first H%T streams get one more.
 DSAC_HD void stream_chunk(int H, int T, int s, int* h0, int* cnt) {

@@ -239,3 +239,6 @@ extern "C" void shim_mt_regenerated(uint32_t seed, int n_blocks, uint32_t* out) 
         for (int k = 0; k < dsac::MT_N; k++) out[r * dsac::MT_N + k] = dsac::mt_temper(sn[k]);
     }
 }
+
+// k_sample's pair-based candidate parser (windows without rejected draws) against the reference loop on the same pairs
+extern "C" int shim_cand_pairs_len(const unsigned short* pr16, int sp, int limit) { return dsac::cand_pairs_len(pr16, sp, limit); }

@@ -70,6 +70,33 @@ def test_block_parallel_mt19937_regeneration_matches_std(oracle, host_shim):
         assert np.array_equal(out, oracle.mt19937_raw(seed, 5 * 624))
 
 
+def test_pair_based_candidate_parser(host_shim):
+    """cand_pairs_len (k_sample's boundary walk): number of (x, y) pairs a minimal set consumes = pairs drawn until four
+    distinct cells are found (cnn_softam.h:1021-1039), incl. repeated cells, long runs of repeats and the end of the window."""
+    rng = np.random.default_rng(21)
+
+    def ref_len(p, sp, limit):
+        seen = []
+        q = sp
+        while len(seen) < 4:
+            if q >= limit:
+                return -1
+            if p[q] not in seen:
+                seen.append(p[q])
+            q += 1
+        return q - sp
+
+    for trial in range(300):
+        n = 64
+        # few distinct values -> many repeats (also more than 4 in a row)
+        vals = rng.integers(0, [1600, 6, 3][trial % 3], n)
+        p = ((vals // 40) << 8 | (vals % 40)).astype(np.uint16)
+        for sp in range(0, n, 3):
+            for limit in (n, min(n, sp + 5), min(n, sp + 9)):
+                got = host_shim.shim_cand_pairs_len(p.ctypes.data_as(C.c_void_p), C.c_int(sp), C.c_int(limit))
+                assert got == ref_len(list(p), sp, limit), (trial, sp, limit)
+
+
 def test_stream_chunk_partition(host_shim):
     for H, T in ((256, 1), (256, 8), (10, 3), (7, 7), (64, 5)):
         covered = []
