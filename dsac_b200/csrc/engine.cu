@@ -20,6 +20,7 @@
 #include "backward.cuh"
 #include "kernels.cuh"
 #include "refine.cuh"
+#include "sampler_split.cuh"
 #include "upstream.cuh"
 
 using namespace dsac;
@@ -88,6 +89,22 @@ struct dsac_engine {
     cudaStream_t hi = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int tail_split = 1;
+    // split sampler (sampler_split.cuh): per-stream state and round buffers, sized at creation
+    int k1_mode = 1;                // 1: round-based pipeline of flat kernels; 0: monolithic k_sample (DSAC_K1_MODE=mono)
+    int k1_rounds = 6, k1_cap = 0;
+    int k1_filter_grid = 0, k1_solve_grid = 0;
+    unsigned long long k1_calls = 0;
+    K1SlotState* d_k1_state = nullptr;
+    CellRec* d_k1_celltab = nullptr;
+    uint2* d_k1_cells = nullptr;
+    uint32_t* d_k1_endw = nullptr;
+    uint32_t* d_k1_accbits = nullptr;
+    double* d_k1_pose = nullptr;
+    uint32_t* d_k1_wq = nullptr;
+    uint32_t* d_k1_fq = nullptr;
+    int* d_k1_counters = nullptr;                 // wq_n[K1S_MAX_ROUNDS], fq_n[K1S_MAX_ROUNDS]
+    unsigned long long* d_k1_stats = nullptr;     // [2][2]: candidates / hypotheses of finished streams, by call parity
+    unsigned long long* d_k1_dbg = nullptr;       // [K1S_MAX_ROUNDS][4] (DSAC_K1_DEBUG=1), else null
 };
 
 static int fail(dsac_engine* e, int code, const char* fmt, ...) {
@@ -158,6 +175,17 @@ void dsac_engine_destroy(dsac_engine* e) {
             fprintf(stderr, "[dsac K1 thread-0 cycles] A1 gen %llu  A2 bounds %llu  B filter %llu  C queue %llu  D full %llu  E advance %llu\n", h[0], h[1], h[2], h[3], h[4], h[5]);
         cudaFree(e->d_phase);
     }
+    if (e->d_k1_dbg) {
+        unsigned long long h[K1S_MAX_ROUNDS * 4];
+        if (cudaMemcpy(h, e->d_k1_dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int r = 0; r < K1S_MAX_ROUNDS && (h[r * 4] || r == 0); r++)
+                fprintf(stderr, "[dsac K1 split, last call] round %d: %llu active streams, %llu candidates, %llu flagged, %llu accepted\n", r,
+                        h[r * 4], h[r * 4 + 1], h[r * 4 + 2], h[r * 4 + 3]);
+    }
+    void* k1ptrs[] = {e->d_k1_state, e->d_k1_celltab, e->d_k1_cells, e->d_k1_endw, e->d_k1_accbits, e->d_k1_pose, e->d_k1_wq,
+                      e->d_k1_fq, e->d_k1_counters, e->d_k1_stats, e->d_k1_dbg};
+    for (void* p : k1ptrs)
+        if (p) cudaFree(p);
     void* ptrs[] = {e->d_coords, e->d_pix, e->d_gt, e->d_perm, e->d_hyp_pose, e->d_hyp_P, e->d_img_idx, e->d_cand_idx,
                     e->d_stream_ncand, e->d_stream_endpos, e->d_ra_frame, e->d_ra_pose, e->d_ra_loss, e->d_ra_rot, e->d_ra_t,
                     e->d_ra_correct, e->d_ra_steps, e->d_ra_imap, e->d_status, e->d_fragile, e->d_diffmaps, e->d_scores, e->d_sf, e->d_entropy,
@@ -276,6 +304,36 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         if (per_sm > 0 && sms > 0) e->k1_slots = per_sm * sms;
     }
     CUC(cudaMallocHost(&e->h_stream_ncand, n * cfg->n_streams * sizeof(long long)));
+    if (const char* m = getenv("DSAC_K1_MODE")) e->k1_mode = (strcmp(m, "mono") == 0) ? 0 : 1;
+    if (const char* r = getenv("DSAC_K1_ROUNDS")) e->k1_rounds = std::max(1, std::min(K1S_MAX_ROUNDS - 1, atoi(r)));
+    if (e->k1_mode) {
+        const size_t T = (size_t)cfg->n_streams, slots = n * T;
+        const int quota_max = (cfg->n_hyps + cfg->n_streams - 1) / cfg->n_streams;
+        int cap = std::min(K1S_MAX_CAP, std::max(256, 64 * quota_max));
+        cap = (cap + 255) & ~255;
+        e->k1_cap = cap;
+        CUC(cudaMalloc(&e->d_k1_state, slots * sizeof(K1SlotState)));
+        CUC(cudaMalloc(&e->d_k1_celltab, n * N * sizeof(CellRec)));
+        CUC(cudaMalloc(&e->d_k1_cells, slots * cap * sizeof(uint2)));
+        CUC(cudaMalloc(&e->d_k1_endw, slots * cap * sizeof(uint32_t)));
+        CUC(cudaMalloc(&e->d_k1_accbits, slots * (cap / 32) * sizeof(uint32_t)));
+        CUC(cudaMalloc(&e->d_k1_pose, slots * cap * 6 * sizeof(double)));
+        CUC(cudaMalloc(&e->d_k1_wq, slots * 64 * sizeof(uint32_t)));
+        CUC(cudaMalloc(&e->d_k1_fq, slots * cap * sizeof(uint32_t)));
+        CUC(cudaMalloc(&e->d_k1_counters, 2 * K1S_MAX_ROUNDS * sizeof(int)));
+        CUC(cudaMalloc(&e->d_k1_stats, 4 * sizeof(unsigned long long)));
+        CUC(cudaMemset(e->d_k1_stats, 0, 4 * sizeof(unsigned long long)));
+        if (getenv("DSAC_K1_DEBUG")) CUC(cudaMalloc(&e->d_k1_dbg, K1S_MAX_ROUNDS * 4 * sizeof(unsigned long long)));
+        CUC(cudaFuncSetAttribute(k1_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1FSmem)));
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_filter, K1F_THREADS, sizeof(K1FSmem));
+        e->k1_filter_grid = std::max(1, per_sm) * e->sm_count;
+        per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_solve, K1V_THREADS, 0);
+        e->k1_solve_grid = std::max(1, per_sm) * e->sm_count;
+        if (const char* g = getenv("DSAC_K1_FILTER_GRID")) e->k1_filter_grid = std::max(1, atoi(g));
+        if (const char* g = getenv("DSAC_K1_SOLVE_GRID")) e->k1_solve_grid = std::max(1, atoi(g));
+    }
     for (int i = 0; i < 4; i++) CUC(cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking));
     {
         int least = 0, greatest = 0;
@@ -345,9 +403,51 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
         sp.stream_ncand = e->d_stream_ncand + o * c.n_streams; sp.stream_endpos = e->d_stream_endpos + o * c.n_streams; sp.status = e->d_status + o; sp.n_fragile = e->d_fragile;
         sp.phase_cycles = e->d_phase;
         { const char* g = getenv("DSAC_K1_A2_GENERIC"); sp.a2_generic = (g && g[0] == '1') ? 1 : 0; }
-        k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);
-        e->launches++;
-        CU(cudaGetLastError());
+        sp.resume = nullptr;
+        if (!e->k1_mode) {
+            k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);
+            e->launches++;
+            CU(cudaGetLastError());
+        } else {
+            // round-based pipeline (sampler_split.cuh).  One pass at a time per engine: the queues are shared.
+            const size_t T = (size_t)c.n_streams, cap = (size_t)e->k1_cap;
+            K1SplitParams q;
+            q.sp = sp;
+            q.state = e->d_k1_state + o * T; q.celltab = e->d_k1_celltab + o * Nn;
+            q.cells = e->d_k1_cells + o * T * cap; q.endw = e->d_k1_endw + o * T * cap;
+            q.accbits = e->d_k1_accbits + o * T * (cap / 32); q.pose_out = e->d_k1_pose + o * T * cap * 6;
+            q.wq = e->d_k1_wq; q.fq = e->d_k1_fq;
+            q.wq_n = e->d_k1_counters; q.fq_n = e->d_k1_counters + K1S_MAX_ROUNDS;
+            const int par = (int)(e->k1_calls & 1ull);
+            e->k1_calls++;
+            q.stats_cur = e->d_k1_stats + 2 * par; q.stats_prev = e->d_k1_stats + 2 * (par ^ 1);
+            q.dbg = e->d_k1_dbg;
+            q.cap = e->k1_cap;
+            const long long n_slots = (long long)n * c.n_streams;
+            q.chunk = std::min(e->k1_cap, n_slots >= 512 ? 2048 : (n_slots >= 64 ? 512 : 256));
+            if (const char* ch = getenv("DSAC_K1_CHUNK")) q.chunk = std::max(256, std::min(std::min(e->k1_cap, K1F_MAX_CHUNK), (atoi(ch) + 255) & ~255));
+            q.n_slots = (int)n_slots;
+            q.round = 0; q.select_only = 0;
+            CU(cudaMemsetAsync(e->d_k1_counters, 0, 2 * K1S_MAX_ROUNDS * sizeof(int), stream));
+            CU(cudaMemsetAsync(q.stats_cur, 0, 2 * sizeof(unsigned long long), stream));
+            if (q.dbg) CU(cudaMemsetAsync(q.dbg, 0, K1S_MAX_ROUNDS * 4 * sizeof(unsigned long long), stream));
+            k1_cells<<<(unsigned)(((size_t)n * Nn + 255) / 256), 256, 0, stream>>>(q, n);
+            e->launches++;
+            const int fgrid = (int)std::min<long long>(e->k1_filter_grid, n_slots * ((e->k1_cap + q.chunk - 1) / q.chunk));
+            for (int r = 0; r < e->k1_rounds; r++) {
+                q.round = r;
+                k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
+                k1_filter<<<fgrid, K1F_THREADS, sizeof(K1FSmem), stream>>>(q);
+                k1_solve<<<e->k1_solve_grid, K1V_THREADS, 0, stream>>>(q);
+                e->launches += 3;
+            }
+            q.round = e->k1_rounds; q.select_only = 1;
+            k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
+            sp.resume = q.state;   // streams the rounds left unfinished (normally none) continue in the monolithic kernel
+            k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);
+            e->launches += 2;
+            CU(cudaGetLastError());
+        }
     }
     if (e->stages & DSAC_STAGE_SCORE) {
         ScoreParams kp;
@@ -412,7 +512,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
 static int forward_split(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* d_coords, const int32_t* d_pix,
                          int32_t pix_shared, const double* d_gt_jp, cudaStream_t stream, bool allow_split) {
     int32_t n1 = 0;
-    if (allow_split && e->tail_split && (e->stages & DSAC_STAGE_SAMPLE) && (e->stages & ~DSAC_STAGE_SAMPLE) && !e->hook) {
+    if (allow_split && e->tail_split && !e->k1_mode && (e->stages & DSAC_STAGE_SAMPLE) && (e->stages & ~DSAC_STAGE_SAMPLE) && !e->hook) {
         const int per_wave = e->k1_slots / std::max(1, e->cfg.n_streams);   // frames per sampler wave
         if (per_wave >= 1 && n > per_wave && n % per_wave != 0) n1 = (n / per_wave) * per_wave;
     }

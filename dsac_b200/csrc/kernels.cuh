@@ -42,6 +42,23 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total, int* s_warp /*
 }
 
 // ------------------------------------------------------------------ K1: sampling
+constexpr int K1S_LEFT_CAP = 2048;               // decoded words carried from one round of the split sampler to the next
+
+// Stream state the split sampler (sampler_split.cuh) carries between its rounds, one per (frame, stream); k_sample
+// resumes from it (SampleParams::resume) for the streams the rounds left unfinished.
+struct K1SlotState {
+    uint32_t mt[624];           // MT19937 state that regenerates the stream words [gen, gen + 624)
+    uint32_t pos, gen;          // next unread stream word; words generated so far (a multiple of 624)
+    int32_t acc;                // hypotheses accepted so far
+    int32_t n_round;            // candidates of the current round
+    int32_t done;               // quota reached
+    int32_t left_n;             // decoded words [pos, gen) kept in left[]
+    int32_t any_reject;         // left[] contains a rejected draw (value 255)
+    int32_t overflow;           // leftover did not fit (cannot happen with the window sizes used; checked by the host)
+    long long cand_base;        // candidates consumed before the current round
+    unsigned char left[K1S_LEFT_CAP];
+};
+
 struct SampleParams {
     const int16_t* coords;   // [n][N][3]
     const int32_t* pix;      // [n or 1][N][2]
@@ -61,6 +78,7 @@ struct SampleParams {
     unsigned long long* n_fragile;  // [1]
     unsigned long long* phase_cycles;  // [8] or null: thread-0 cycles per phase (development aid)
     int a2_generic;                    // 1: always take the general boundary path (test aid, DSAC_K1_A2_GENERIC=1)
+    const K1SlotState* resume;         // null: streams start at their seed; else continue the split sampler's streams
 };
 
 #ifndef K1_THREADS_DEF
@@ -181,8 +199,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
         return;
     }
 
+    const K1SlotState* rs = p.resume ? p.resume + ((size_t)frame * p.T + s) : nullptr;
+    if (rs && rs->done) return;
     // stream s of global frame g: mt19937(seed + g*T + s)   (thread_rand.cpp:52 for g = 0)
-    if (tid == 0) mt_seed(sm.st, p.seed + (uint32_t)((p.frame0 + frame) * (long long)p.T + s));
+    if (!rs && tid == 0) mt_seed(sm.st, p.seed + (uint32_t)((p.frame0 + frame) * (long long)p.T + s));
 
     const int16_t* coords = p.coords + (size_t)frame * DSAC_N_CONST * 3;
     const int32_t* pix = p.pix + (size_t)frame * p.pix_stride;
@@ -199,13 +219,22 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
             sm.cell[c] = r;
         }
     }
-    if (tid == 0) { sm.any_reject = 0; sm.walk_fail = 0; }
-    __syncthreads();
-
+    if (tid == 0) { sm.any_reject = rs ? rs->any_reject : 0; sm.walk_fail = 0; }
     uint32_t pos = (s == 0) ? p.skip : 0u;  // stream position (output word index) of the next unread word
     uint32_t gen = 0;                       // output words generated so far (linear MT index = gen + 624)
     int acc = 0;                            // hypotheses accepted so far
     long long cand_base = 0;                // candidates consumed so far
+#if K1_GEN624
+    if (rs) {   // continue where the split sampler's last round stopped
+        pos = rs->pos; gen = rs->gen; acc = rs->acc; cand_base = rs->cand_base;
+        uint32_t* half = sm.st + ((gen / MT_N) & 1u) * MT_N;
+        for (int k = tid; k < MT_N; k += K1_THREADS) half[k] = rs->mt[k];
+        const int ln = rs->left_n;
+        for (int k = tid; k < ln; k += K1_THREADS) sm.vals[k] = rs->left[k];
+    }
+#endif
+    __syncthreads();
+
     const long long cand_max = p.max_candidates > 0 ? (long long)p.max_candidates : (1ll << 40);
     int S = 4;                              // x256 candidates in the next super-round (adapted to the acceptance rate)
 
