@@ -283,6 +283,45 @@ DSAC_HD double rsqrt_or(double x) {
 #endif
 }
 
+// Reciprocal / reciprocal square root / square root for the CONSERVATIVE FILTER only (quartic_roots_banded, p3p_quick_core):
+// the hardware's 20-bit approximation refined by two Newton steps -- a few ulp, five to nine instructions instead of the
+// IEEE division / square root sequences (which were ~30 % of the filter's instructions).  The filter's decisions are
+// protected by bands >= 1e-9 relative (and 0.05 px), nine orders of magnitude above that error; zero, subnormal, infinite
+// or NaN arguments give inf / NaN, which every test of the filter sends to "needs the full solve".  The full solve and
+// everything that produces results keeps IEEE arithmetic.  On the host these are the exact operations.
+DSAC_HD double filt_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+DSAC_HD double filt_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h, y * y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h, y * y, 0.5);
+    return fma(y, e, y);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+DSAC_HD double filt_sqrt(double x) {   // x > 0
+#if defined(__CUDA_ARCH__)
+    return x * filt_rsqrt(x);
+#else
+    return sqrt(x);
+#endif
+}
+
 // quartic_roots with an "uncertain" verdict: set when any sign decision of Ferrari's method lies
 // within a relative band of 1e-9 (>= 10^6 x double rounding), i.e. when another instance of the same
 // computation with different rounding could decide differently.  Used by the conservative filter.
@@ -313,7 +352,7 @@ DSAC_HD double cubic_first_root_seeded(double a2, double a1, double a0, bool* ok
 #pragma unroll
     for (int it = 0; it < 3; it++) {
         const double g = ((y + a2) * y + a1) * y + a0, gp = (3 * y + 2 * a2) * y + a1;
-        dy = g / gp;
+        dy = g * filt_rcp(gp);
         y -= dy;
     }
     *ok = fabs(dy) <= 1e-9 * (fabs(y) + fabs(sh));
@@ -323,7 +362,7 @@ DSAC_HD double cubic_first_root_seeded(double a2, double a1, double a0, bool* ok
 DSAC_HD int quartic_roots_banded(double a, double b, double c, double d, double e, double x[4], bool* uncertain) {
     const double TOL = 1e-9;
     *uncertain = false;
-    double ia = 1.0 / a;
+    double ia = filt_rcp(a);
     b *= ia; c *= ia; d *= ia; e *= ia;
     bool cubic_ok;
     double y1 = cubic_first_root_seeded(-c, d * b - 4 * e, 4 * c * e - d * d - b * b * e, &cubic_ok);
@@ -331,20 +370,20 @@ DSAC_HD int quartic_roots_banded(double a, double b, double c, double d, double 
     double R2 = 0.25 * b * b - c + y1, mR = 0.25 * b * b + fabs(c) + fabs(y1);
     if (!(fabs(R2) > TOL * mR)) { *uncertain = true; return 0; }   // also catches NaN and the R ~ 0 branch
     if (R2 < 0) return 0;
-    double R = sqrt(R2);
+    double R = filt_sqrt(R2);
     double u = 0.75 * b * b - 2 * c - R2;
-    double v = 0.25 * (4 * b * c - 8 * d - b * b * b) / R;
+    double v = 0.25 * (4 * b * c - 8 * d - b * b * b) * filt_rcp(R);
     double D2 = u + v, E2 = u - v, mD = fabs(0.75 * b * b) + fabs(2 * c) + R2 + fabs(v);
     if (!(fabs(D2) > TOL * mD) || !(fabs(E2) > TOL * mD)) { *uncertain = true; return 0; }
     int n = 0;
     if (D2 > 0) {
-        double Dq = sqrt(D2);
+        double Dq = filt_sqrt(D2);
         x[0] = 0.5 * R + 0.5 * Dq - 0.25 * b;
         x[1] = x[0] - Dq;
         n = 2;
     }
     if (E2 > 0) {
-        double Eq = sqrt(E2);
+        double Eq = filt_sqrt(E2);
         x[n] = -0.5 * R + 0.5 * Eq - 0.25 * b;
         x[n + 1] = x[n] - Eq;
         n += 2;
@@ -717,7 +756,7 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
     const double p = 2 * (bear[1][0] * bear[2][0] + bear[1][1] * bear[2][1] + bear[1][2] * bear[2][2]);
     const double q = 2 * (bear[0][0] * bear[2][0] + bear[0][1] * bear[2][1] + bear[0][2] * bear[2][2]);
     const double r = 2 * (bear[0][0] * bear[1][0] + bear[0][1] * bear[1][1] + bear[0][2] * bear[1][2]);
-    const double inv_c2 = 1.0 / s01;
+    const double inv_c2 = filt_rcp(s01);
     const double a = inv_c2 * s12, b = inv_c2 * s02;
     if (!(fabs(p * p + q * q + r * r - p * q * r - 1) > 1e-12)) return DSAC_FLAG(2);
     const double N2 = 1 - a - b, N1 = q * (a - 1), N0 = 1 - a + b;
@@ -739,7 +778,7 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
     }
     if (nroots == 0) return false;   // no real root, by a margin no rounding can bridge
     // world triangle frame and the 4th point's coordinates in it
-    const double inv_d = rsqrt_or(s01), inv_n = rsqrt_or(nn), d01 = s01 * inv_d;
+    const double inv_d = filt_rsqrt(s01), inv_n = filt_rsqrt(nn), d01 = s01 * inv_d;
     const double e1x = ax * inv_d, e1y = ay * inv_d, e1z = az * inv_d;
     const double e3x = nx * inv_n, e3y = ny * inv_n, e3z = nz * inv_n;
     const double e2x = e3y * e1z - e3z * e1y, e2y = e3z * e1x - e3x * e1z, e2z = e3x * e1y - e3y * e1x;
@@ -751,7 +790,7 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         double x = xr[i];
         const double Dn = D1 * x + D0;
         if (!(fabs(Dn) > 1.1e-3 * (fabs(D1 * x) + fabs(D0)))) return DSAC_FLAG(5);   // (the full solve switches formula at 1e-3)
-        double y = -((N2 * x + N1) * x + N0) / Dn;
+        double y = -((N2 * x + N1) * x + N0) * filt_rcp(Dn);
         const double f1 = (1 - a) * y * y - a * x * x - p * y + a * r * x * y + 1;
         const double f2 = (1 - b) * x * x - b * y * y - q * x + b * r * x * y + 1;
         const double j11 = -2 * a * x + a * r * y, j12 = 2 * (1 - a) * y - p + a * r * x;
@@ -759,7 +798,7 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         const double det = j11 * j22 - j12 * j21;
         const double jn = j11 * j11 + j12 * j12 + j21 * j21 + j22 * j22;
         if (!(fabs(det) > 1e-4 * jn)) return DSAC_FLAG(6);
-        const double idet = 1.0 / det;
+        const double idet = filt_rcp(det);
         const double dx = (f1 * j22 - f2 * j12) * idet, dy = (j11 * f2 - j21 * f1) * idet;
         x -= dx;
         y -= dy;
@@ -768,7 +807,7 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         if (x < 1e-6 || y < 1e-6) return DSAC_FLAG(8);
         const double v = x * x + y * y - x * y * r;
         if (!(v > 1e-12)) return DSAC_FLAG(9);
-        const double Z = d01 * rsqrt_or(v);
+        const double Z = d01 * filt_rsqrt(v);
         const double L0 = x * Z, L1 = y * Z;
         const double M0x = L0 * bear[0][0], M0y = L0 * bear[0][1], M0z = L0 * bear[0][2];
         const double ux = L1 * bear[1][0] - M0x, uy = L1 * bear[1][1] - M0y, uz = L1 * bear[1][2] - M0z;

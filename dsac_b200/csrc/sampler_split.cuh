@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) k1_cells(K1SplitParams q, int n_frames) {
 // ------------------------------------------------------------------ k1_slot
 struct K1GSmem {
     uint32_t st[2 * MT_N];                       // MT19937 state, double-buffered (old / new generation)
-    __align__(4) unsigned char vals[K1S_WORDS];  // Lemire value (0..39) of stream word pos+i; 255 = rejected draw
+    __align__(16) unsigned char vals[K1S_WORDS];  // Lemire value (0..39) of stream word pos+i; 255 = rejected draw
     unsigned short cand_start[K1S_SR + 512];     // word offset (from pos) where candidate i starts
     unsigned short acc_list[K1S_ACC_LIST];       // selection: accepted candidates of the round, in order
     int warp[2][K1S_WARPS];
@@ -237,13 +237,15 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
 
     // ---------------- generation: windows of up to K1S_SR candidates (phases A1, A2 and E of k_sample)
     int produced = 0;
+    uint32_t st_par = (gen / MT_N) & 1u;   // which half of sm.st holds the current state
     while (produced < n_round) {
         const int n_target = min(K1S_SR, n_round - produced);
         const int w_need = min(K1S_WORDS - 640, n_target * 8 + 768);   // a regeneration may overshoot by 623 words
         // (leftover words [pos, gen) are at vals[0..gen-pos))
         while ((int)(gen - pos) < w_need) {
-            const uint32_t* so = sm.st + ((gen / MT_N) & 1u) * MT_N;           // old state
-            uint32_t* sn = sm.st + (((gen / MT_N) & 1u) ^ 1u) * MT_N;            // new state
+            const uint32_t* so = sm.st + st_par * MT_N;           // old state
+            uint32_t* sn = sm.st + (st_par ^ 1u) * MT_N;            // new state
+            st_par ^= 1u;
             if (tid < K1_WAVE) {
                 uint32_t x[3];
                 const bool has3 = mt_regenerate_words(so, tid, x) == 3;
@@ -272,26 +274,61 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
         if (!sm.any_reject && !p.a2_generic) {
             const unsigned short* pr16 = reinterpret_cast<const unsigned short*>(sm.vals);
             const int scan_end = min(w_avail >> 1, n_target * 4 + 384);
-            const int seg = (((scan_end + K1S_WARPS - 1) / K1S_WARPS) + 31) & ~31;
-            const int wbeg = warp_id * seg, wend = min(wbeg + seg, scan_end);
+            // Every thread takes 16-byte blocks (8 pairs = 4 words of 2 pairs) and compares each word with the three
+            // preceding pairs two pairs at a time (zero-half test on the XOR with the shifted predecessors, ~7
+            // instructions per pair); only blocks that contain a repeat (~1 in 60) go through the recording path.
+            const uint4* v128 = reinterpret_cast<const uint4*>(sm.vals);
+            const int n_blocks = (scan_end + 7) >> 3;
+            const int bseg = ((n_blocks + K1S_WARPS - 1) / K1S_WARPS + 31) & ~31;   // blocks per warp, contiguous: events stay ordered
+            const int bbeg = warp_id * bseg, bend = min(bbeg + bseg, n_blocks);
             int cnt = 0;
-            for (int k0 = wbeg; k0 < wend; k0 += 32) {
-                const int k = k0 + lane;
-                const unsigned pk = (k < scan_end) ? pr16[k] : 0xffffu;
-                unsigned p1 = __shfl_up_sync(0xffffffffu, pk, 1), p2 = __shfl_up_sync(0xffffffffu, pk, 2), p3 = __shfl_up_sync(0xffffffffu, pk, 3);
-                if (lane < 3) {
-                    if (lane < 1) p1 = (k >= 1) ? pr16[k - 1] : 0xffffu;
-                    if (lane < 2) p2 = (k >= 2) ? pr16[k - 2] : 0xffffu;
-                    p3 = (k >= 3) ? pr16[k - 3] : 0xffffu;
+            for (int b0 = bbeg; b0 < bend; b0 += 32) {
+                const int b = b0 + lane;
+                uint32_t w[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // w[0..1]: the two words before the block
+                if (b < bend) {
+                    const uint4 cur = v128[b];
+                    w[2] = cur.x; w[3] = cur.y; w[4] = cur.z; w[5] = cur.w;
+                    if (b > 0) {
+                        const uint2 prv = *reinterpret_cast<const uint2*>(sm.vals + 16 * b - 8);
+                        w[0] = prv.x; w[1] = prv.y;
+                    }
                 }
-                unsigned d = 0;
-                if (k < wend) d = (pk == p1) ? 1u : (pk == p2) ? 2u : (pk == p3) ? 3u : 0u;
-                const unsigned m = __ballot_sync(0xffffffffu, d != 0);
-                if (d) {
-                    const int sl = cnt + __popc(m & ((1u << lane) - 1u));
-                    if (sl < K1_EV_CAP) sm.ev[warp_id][sl] = ((uint32_t)k << 2) | d;
+                uint32_t any = 0;
+#pragma unroll
+                for (int j2 = 2; j2 < 6; j2++) {
+                    const uint32_t s1 = __funnelshift_l(w[j2 - 1], w[j2], 16);       // (pair 2j-1, pair 2j)
+                    const uint32_t s3 = __funnelshift_l(w[j2 - 2], w[j2 - 1], 16);   // (pair 2j-3, pair 2j-2)
+                    const uint32_t x1 = w[j2] ^ s1, x2 = w[j2] ^ w[j2 - 1], x3 = w[j2] ^ s3;
+                    any |= ((x1 - 0x00010001u) & ~x1) | ((x2 - 0x00010001u) & ~x2) | ((x3 - 0x00010001u) & ~x3);
                 }
-                cnt += __popc(m);
+                const bool has = (b < bend) && (any & 0x80008000u) != 0u;
+                if (__any_sync(0xffffffffu, has)) {   // rare: record (pair index, distance) in pair order
+                    uint32_t evs[8];
+                    int ne = 0;
+                    if (has) {
+#pragma unroll
+                        for (int h2 = 0; h2 < 8; h2++) {
+                            const int k = 8 * b + h2;
+                            const uint32_t wj = w[2 + (h2 >> 1)], wp1 = w[1 + (h2 >> 1)], wp2 = w[(h2 >> 1)];
+                            uint32_t pk, q1, q2, q3;
+                            if (h2 & 1) { pk = wj >> 16; q1 = wj & 0xffffu; q2 = wp1 >> 16; q3 = wp1 & 0xffffu; }
+                            else { pk = wj & 0xffffu; q1 = wp1 >> 16; q2 = wp1 & 0xffffu; q3 = wp2 >> 16; }
+                            const uint32_t d = (pk == q1) ? 1u : (pk == q2) ? 2u : (pk == q3) ? 3u : 0u;
+                            if (d && k < scan_end) evs[ne++] = ((uint32_t)k << 2) | d;
+                        }
+                    }
+                    int incl = ne;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (lane >= off) incl += o;
+                    }
+                    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                    const int at = cnt + incl - ne;
+                    for (int e = 0; e < ne; e++)
+                        if (at + e < K1_EV_CAP) sm.ev[warp_id][at + e] = evs[e];
+                    cnt += tot;
+                }
             }
             if (lane == 0) sm.ev_n[warp_id] = cnt;
             __syncthreads();
@@ -468,74 +505,67 @@ __device__ __forceinline__ bool k1_filter_candidate(const CellRec* cell, const i
 #endif
 struct K1FSmem {
     CellRec cell[DSAC_N_CONST];
-    uint32_t flagbits[K1F_MAX_CHUNK / 32];
-    int q_n;
-    int q_at;
+    unsigned short wlist[K1F_THREADS / 32][K1F_MAX_CHUNK / (K1F_THREADS / 32)];   // per warp: flagged candidates of its share of the item
 };
 
+// One work item = up to `chunk` consecutive candidates of one stream.  The CTA stages the frame's cell table (only when
+// the frame changes); after that its warps run independently: a warp filters every 8th group of 32 candidates of the
+// item (coalesced 8-byte loads of the cell indices, the next group's prefetched), keeps the flagged ones in its own
+// list and appends them to the global queue with one atomic per item.  No block barrier except around the staging.
 __global__ void __launch_bounds__(K1F_THREADS, K1F_MIN_BLOCKS) k1_filter(K1SplitParams q) {
     extern __shared__ __align__(16) unsigned char k1f_smem_raw[];
     K1FSmem& sm = *reinterpret_cast<K1FSmem*>(k1f_smem_raw);
     const SampleParams& p = q.sp;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp_id = tid >> 5;
     const int n_items = q.wq_n[q.round];
     const double inv_f = 1. / p.f, cx_f = p.cx * inv_f, cy_f = p.cy * inv_f;
+    unsigned short* wl = sm.wlist[warp_id];
     int staged_frame = -1;
+    unsigned long long n_flagged = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t it = q.wq[item];
         const int slot = (int)(it >> 6), chunk = (int)(it & 63u);
         const int frame = slot / p.T;
         if (frame != staged_frame) {   // the frame's cell table (38.4 KB) to shared memory
+            __syncthreads();
             const uint4* src = reinterpret_cast<const uint4*>(q.celltab + (size_t)frame * DSAC_N_CONST);
             uint4* dst = reinterpret_cast<uint4*>(sm.cell);
             for (int k = tid; k < (int)(sizeof(CellRec) * DSAC_N_CONST / 16); k += K1F_THREADS) dst[k] = __ldg(src + k);
             staged_frame = frame;
+            __syncthreads();
         }
-        __syncthreads();
         const int n_round = q.state[slot].n_round;
         const int base = chunk * q.chunk;
         const int n_here = min(q.chunk, n_round - base);
         const uint2* cc = q.cells + (size_t)slot * q.cap + base;
-        for (int i0 = 0; i0 < n_here; i0 += K1F_THREADS) {
-            const int i = i0 + tid;
+        int cnt = 0;
+        int i = warp_id * 32 + lane;
+        uint2 c = (i < n_here) ? __ldg(cc + i) : make_uint2(0u, 0u);
+        for (int i0 = warp_id * 32; i0 < n_here; i0 += K1F_THREADS) {
+            i = i0 + lane;
+            const int in = i + K1F_THREADS;
+            const uint2 cn = (in < n_here) ? __ldg(cc + in) : make_uint2(0u, 0u);   // next group's cell indices
             bool need = false;
             if (i < n_here) {
-                const uint2 c = __ldg(cc + i);
                 const int cells[4] = {(int)(c.x & 0xffffu), (int)(c.x >> 16), (int)(c.y & 0xffffu), (int)(c.y >> 16)};
                 need = k1_filter_candidate(sm.cell, cells, p.f, p.cx, p.cy, inv_f, cx_f, cy_f, (double)p.thr);
             }
             const uint32_t bits = __ballot_sync(0xffffffffu, need);
-            if (lane == 0) sm.flagbits[i >> 5] = bits;
+            if (need) wl[cnt + __popc(bits & ((1u << lane) - 1u))] = (unsigned short)(base + i);
+            cnt += __popc(bits);
+            c = cn;
         }
-        __syncthreads();
-        // flagged candidates of the item, in order, to the global queue (one atomic per item)
-        const int n_words = (n_here + 31) >> 5;   // <= chunk / 32 <= 512
-        if (tid < 32) {
-            int sum = 0;
-            for (int w = tid; w < n_words; w += 32) sum += __popc(sm.flagbits[w]);
-#pragma unroll
-            for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-            if (tid == 0) {
-                sm.q_n = sum;
-                sm.q_at = sum ? atomicAdd(q.fq_n + q.round, sum) : 0;
-            }
+        __syncwarp();
+        if (cnt > 0) {
+            int at = 0;
+            if (lane == 0) at = atomicAdd(q.fq_n + q.round, cnt);
+            at = __shfl_sync(0xffffffffu, at, 0);
+            for (int k = lane; k < cnt; k += 32) q.fq[at + k] = ((uint32_t)slot << 14) | (uint32_t)wl[k];
+            n_flagged += (unsigned long long)cnt;
         }
-        __syncthreads();
-        if (sm.q_n > 0) {
-            // word w's entries start at q_at + (number of flagged in words < w): every warp recomputes the short prefix it needs
-            for (int w = tid >> 5; w < n_words; w += K1F_THREADS / 32) {
-                int before = 0;
-                for (int v = lane; v < w; v += 32) before += __popc(sm.flagbits[v]);
-#pragma unroll
-                for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xffffffffu, before, off);
-                const uint32_t wb = sm.flagbits[w];
-                if ((wb >> lane) & 1u)
-                    q.fq[sm.q_at + before + __popc(wb & ((1u << lane) - 1u))] = ((uint32_t)slot << 14) | (uint32_t)(base + w * 32 + lane);
-            }
-            if (q.dbg && tid == 0) atomicAdd(q.dbg + (size_t)q.round * 4 + 2, (unsigned long long)sm.q_n);
-        }
-        __syncthreads();
+        __syncwarp();
     }
+    if (q.dbg && lane == 0 && n_flagged) atomicAdd(q.dbg + (size_t)q.round * 4 + 2, n_flagged);
 }
 
 // ------------------------------------------------------------------ k1_solve

@@ -53,17 +53,17 @@ inline void lua_createtable(lua_State* L, int narr, int) {
     x.tab->reserve(narr > 0 ? narr : 0);
     L->stack.push_back(std::move(x));
 }
-inline void lua_rawseti(lua_State* L, int idx, int n) {   // t[n] = top; pops the value
+inline void lua_rawseti(lua_State* L, int idx, int n) {   // t[n] = top; pops the value (idx is resolved with the value still on the stack)
+    std::shared_ptr<std::vector<double>> t = shim_lua_at(L, idx).tab;
     const double v = L->stack.back().num;
     L->stack.pop_back();
-    std::vector<double>& t = *shim_lua_at(L, idx).tab;
-    if ((int)t.size() < n) t.resize(n, 0.0);
-    t[n - 1] = v;
+    if ((int)t->size() < n) t->resize(n, 0.0);
+    (*t)[n - 1] = v;
 }
-inline void lua_gettable(lua_State* L, int idx) {   // key = top (popped); pushes t[key]
+inline void lua_gettable(lua_State* L, int idx) {   // key = top (popped); pushes t[key] (idx is resolved with the key still on the stack)
+    const shim_lua_value t = shim_lua_at(L, idx);
     const int key = (int)L->stack.back().num;
     L->stack.pop_back();
-    const shim_lua_value& t = shim_lua_at(L, idx);
     double v = 0;
     if (t.kind == shim_lua_value::TABLE && key >= 1 && key <= (int)t.tab->size()) v = (*t.tab)[key - 1];
     lua_pushnumber(L, v);

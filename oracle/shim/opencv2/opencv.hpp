@@ -18,6 +18,7 @@
 // rv.at<double>(0,1) of a 3x1 matrix).
 #pragma once
 #include <algorithm>
+#include <cassert>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -46,10 +47,14 @@
 
 enum { CV_ITERATIVE = 0, CV_EPNP = 1, CV_P3P = 2 };
 
-namespace cv {
-
+// OpenCV's C headers put these in the global namespace (core/types_c.h); the reference relies on it (types.h:47)
 typedef unsigned char uchar;
 typedef unsigned short ushort;
+
+namespace cv {
+
+using ::uchar;
+using ::ushort;
 
 // ---------------------------------------------------------------- saturate_cast (cv::saturate_cast semantics: round to nearest even, clamp)
 template <typename T> inline T saturate_cast(double v) { return (T)v; }
@@ -206,6 +211,10 @@ public:
 
     void create(int r, int c, int type) {
         if (data && rows == r && cols == c && type_ == type) return;
+        // cv::Mat::create raises cv::Exception (a std::exception) for impossible sizes; the reference relies on that
+        // when it probes for ./sensorTrans.dat (properties.cpp:79-90 reads rows / cols from a stream that failed to open)
+        if (r < 0 || c < 0 || (double)r * (double)c * (double)(shim_depth_size(CV_MAT_DEPTH(type)) * CV_MAT_CN(type)) > 1.0e9)
+            throw std::runtime_error("shim: cv::Mat::create with an impossible size");
         rows = r; cols = c; type_ = type;
         const size_t es = elemSize();
         step = (size_t)c * es;
