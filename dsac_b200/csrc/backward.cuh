@@ -131,6 +131,10 @@ struct BwParams {
     // (zeroed by the caller) and k_dscore_reduce adds the groups to s.row in order
     double* part;
     int groups;
+    // score seam, adjoint side (lua_calls.h:312-341): when set, dScore/dDiffMap of every hypothesis comes from the
+    // registered backward hook -- [n][H][40][40] doubles, element (y, x) as the reference's gradients[c](y, x) -- instead
+    // of the closed-form derivative of the soft-inlier score
+    const double* ext_g;
 };
 
 // ------------------------------------------------------------------ DSAC / RANSAC variant (train_ransac.cpp:304-381)
@@ -487,6 +491,16 @@ inline int dscore_groups(int n_frames, int n_hyps, int sm_count) {
     return std::max(1, g);
 }
 
+// scoreOutputGradients clamped to +-clamp, as the reference's score backward does before back-propagating
+// (train_score_softam.lua:97) -- the copy a registered backward hook receives
+__global__ void k_clamp_copy(const double* __restrict__ src, double* __restrict__ dst, size_t count, double clamp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double v = src[i];
+    if (clamp > 0) v = fmax(-clamp, fmin(clamp, v));
+    dst[i] = v;
+}
+
 __global__ void k_dscore_reduce(BwParams p) {
     const int frame = blockIdx.x;
     double* row = p.s.row + (size_t)frame * DSAC_N_CONST * 3;
@@ -539,8 +553,13 @@ __global__ void __launch_bounds__(K5_THREADS) k_dscore(BwParams p) {
             float pfu = (float)__dadd_rn(__dmul_rn(__dmul_rn(xc, iz), f), cx), pfv = (float)__dadd_rn(__dmul_rn(__dmul_rn(yc, iz), f), cy);
             float du = __fsub_rn((float)pu[j], pfu), dv = __fsub_rn((float)pv[j], pfv);
             double e = (double)(float)fmin(sqrt(__dadd_rn(__dmul_rn((double)du, (double)du), __dmul_rn((double)dv, (double)dv))), 100.0);
-            double sg = 1.0 / (1.0 + exp(-p.beta * ((double)p.thr - e)));
-            double g = go * (-p.alpha * p.beta * sg * (1.0 - sg));   // dDiffMaps[h](y,x) under the soft-inlier score
+            double g;
+            if (p.ext_g) {
+                g = p.ext_g[((size_t)frame * p.H + h) * DSAC_N_CONST + tid + j * K5_THREADS];   // backward hook's dDiffMaps[h](y,x)
+            } else {
+                double sg = 1.0 / (1.0 + exp(-p.beta * ((double)p.thr - e)));
+                g = go * (-p.alpha * p.beta * sg * (1.0 - sg));   // dDiffMaps[h](y,x) under the soft-inlier score
+            }
             // --- dProjectdObj / dProjectdHyp in the jp convention (cnn_softam.h:404-528)
             double ex = R[0] * X[j] + R[1] * Y[j] + R[2] * Z[j] + t[0];
             double ey = R[3] * X[j] + R[4] * Y[j] + R[5] * Z[j] + t[1];

@@ -34,6 +34,13 @@ struct dsac_engine {
     uint32_t stages = DSAC_STAGE_ALL;
     dsac_score_hook hook = nullptr;
     void* hook_user = nullptr;
+    dsac_score_backward_hook bw_hook = nullptr;
+    void* bw_hook_user = nullptr;
+    double* d_ext_g = nullptr;      // [n][H][N] dScore/dDiffMap from the backward hook (grow-only)
+    size_t ext_g_count = 0;
+    cudaEvent_t ev_fwd = nullptr;   // recorded after the last forward launch: the backward waits on it
+    double* d_kabsch = nullptr;     // dsac_kabsch: inputs and outputs in one grow-only block
+    size_t kabsch_bytes = 0;
     int sm_count = 148;
     // inputs (device copies for the host-buffer entry point)
     int16_t* d_coords = nullptr;
@@ -169,6 +176,9 @@ void dsac_engine_destroy(dsac_engine* e) {
     if (e->hi) { cudaStreamSynchronize(e->hi); cudaStreamDestroy(e->hi); }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_fwd) cudaEventDestroy(e->ev_fwd);
+    if (e->d_ext_g) cudaFree(e->d_ext_g);
+    if (e->d_kabsch) cudaFree(e->d_kabsch);
     if (e->d_phase) {
         unsigned long long h[16];
         if (cudaMemcpy(h, e->d_phase, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -341,6 +351,7 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         CUC(cudaStreamCreateWithPriority(&e->hi, cudaStreamNonBlocking, greatest));
         CUC(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&e->ev_fwd, cudaEventDisableTiming));
         if (const char* ts = getenv("DSAC_TAIL_SPLIT")) e->tail_split = atoi(ts);
     }
 #undef CUC
@@ -368,6 +379,40 @@ int dsac_set_score_hook(dsac_engine* e, dsac_score_hook fn, void* user) {
     if (fn && !e->cfg.write_diffmaps) return fail(e, DSAC_ERR_ARG, "a score hook needs write_diffmaps=1");
     e->hook = fn;
     e->hook_user = user;
+    return DSAC_OK;
+}
+
+int dsac_set_score_backward_hook(dsac_engine* e, dsac_score_backward_hook fn, void* user) {
+    if (!e) return DSAC_ERR_ARG;
+    e->bw_hook = fn;
+    e->bw_hook_user = user;
+    return DSAC_OK;
+}
+
+// Score seam in the backward pass: with hooks registered, dScore/dDiffMap comes from the backward hook (fills e->d_ext_g);
+// returns the pointer k_dscore shall read (null: closed-form soft-inlier derivative).
+static int seam_backward(dsac_engine* e, int n, const double* d_sog, cudaStream_t stream, const double** ext_g) {
+    *ext_g = nullptr;
+    if (!e->hook && !e->bw_hook) return DSAC_OK;
+    if (!e->hook || !e->bw_hook)
+        return fail(e, DSAC_ERR_ARG, "the score seam needs both hooks: %s is registered but %s is not (dsac_set_score_hook / dsac_set_score_backward_hook)",
+                    e->hook ? "the forward hook" : "the backward hook", e->hook ? "the backward hook" : "the forward hook");
+    if (!e->d_diffmaps) return fail(e, DSAC_ERR_ARG, "the score seam needs write_diffmaps=1");
+    const size_t H = e->cfg.n_hyps, count = (size_t)n * H * DSAC_N;
+    if (count > e->ext_g_count) {
+        if (e->d_ext_g) cudaFree(e->d_ext_g);
+    if (e->d_kabsch) cudaFree(e->d_kabsch);
+        e->d_ext_g = nullptr; e->ext_g_count = 0;
+        CU(cudaMalloc(&e->d_ext_g, (count + (size_t)n * H) * sizeof(double)));
+        e->ext_g_count = count;
+    }
+    double* clamped = e->d_ext_g + e->ext_g_count;   // [n][H] behind the gradient block
+    k_clamp_copy<<<(unsigned)(((size_t)n * H + 255) / 256), 256, 0, stream>>>(d_sog, clamped, (size_t)n * H, e->cfg.grad_clamp);
+    e->launches++;
+    CU(cudaGetLastError());
+    int rc = e->bw_hook(e->d_diffmaps, clamped, n, (int32_t)H, e->d_ext_g, (void*)stream, e->bw_hook_user);
+    if (rc != 0) return fail(e, DSAC_ERR_ARG, "score backward hook returned %d", rc);
+    *ext_g = e->d_ext_g;
     return DSAC_OK;
 }
 
@@ -521,13 +566,14 @@ static int forward_split(dsac_engine* e, int32_t n, int64_t frame0, const int16_
     CU(cudaEventRecord(e->ev_fork, stream));
     CU(cudaStreamWaitEvent(e->hi, e->ev_fork, 0));
     int rc = forward_range(e, 0, n1, frame0, d_coords, d_pix, pix_shared, d_gt_jp, e->hi);
-    if (rc != DSAC_OK) return rc;
-    CU(cudaEventRecord(e->ev_join, e->hi));
-    rc = forward_range(e, n1, n - n1, frame0 + n1, d_coords + f * N * 3, pix_shared ? d_pix : d_pix + f * N * 2, pix_shared,
-                       d_gt_jp ? d_gt_jp + f * 12 : nullptr, stream);
-    if (rc != DSAC_OK) return rc;
+    // whatever happens below, the caller's stream joins the side stream again: nothing may still be writing engine
+    // buffers on e->hi when the caller sees this call's work as complete (or its error)
+    cudaEventRecord(e->ev_join, e->hi);
+    if (rc == DSAC_OK)
+        rc = forward_range(e, n1, n - n1, frame0 + n1, d_coords + f * N * 3, pix_shared ? d_pix : d_pix + f * N * 2, pix_shared,
+                           d_gt_jp ? d_gt_jp + f * 12 : nullptr, stream);
     CU(cudaStreamWaitEvent(stream, e->ev_join, 0));
-    return DSAC_OK;
+    return rc;
 }
 
 int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* d_coords, const int32_t* d_pix,
@@ -543,7 +589,11 @@ int dsac_forward_device(dsac_engine* e, int32_t n, int64_t frame0, const int16_t
     e->cur_n = n;
     e->dsac_n = 0;
     e->cur_frame0 = frame0;
-    return forward_split(e, n, frame0, d_coords, d_pix, pix_shared, d_gt_jp, (cudaStream_t)stream_v, true);
+    if (e->pending_chunks) return fail(e, DSAC_ERR_ARG, "dsac_forward_device: a submitted pass has not been awaited (dsac_forward_wait)");
+    int rc = forward_split(e, n, frame0, d_coords, d_pix, pix_shared, d_gt_jp, (cudaStream_t)stream_v, true);
+    if (rc != DSAC_OK) return rc;
+    CU(cudaEventRecord(e->ev_fwd, (cudaStream_t)stream_v));   // dsac_backward (engine stream) waits on this
+    return DSAC_OK;
 }
 
 // Queues the device->host copies of frames [off, off+n) into the caller's buffers (no synchronisation).
@@ -671,17 +721,21 @@ static int forward_submit_impl(dsac_engine* e, int32_t n, int64_t frame0, const 
                                      blocking ? e->tail_split >= 1 : e->tail_split >= 2)
                      : forward_range(e, lo, m, frame0 + lo, e->d_coords + f * N * 3, pix_shared ? e->d_pix : e->d_pix + f * N * 2,
                                      pix_shared, gt_jp ? e->d_gt + f * 12 : nullptr, st);
-        if (rc != DSAC_OK) return rc;
-        if (trace) cudaEventRecord(tev[2], st);
-        if (out) {
+        if (rc == DSAC_OK && out) {
+            if (trace) cudaEventRecord(tev[2], st);
             rc = fetch_range(e, lo, m, out, st);
-            if (rc != DSAC_OK) return rc;
         }
+        if (rc != DSAC_OK) {   // copies from the caller's host buffers may already be queued: drain before reporting
+            for (int k = 0; k <= c; k++) cudaStreamSynchronize(e->pipe[k]);
+            return rc;
+        }
+        if (trace && !out) cudaEventRecord(tev[2], st);
         if (trace) cudaEventRecord(tev[3], st);
     }
     e->pending_out = out;
     e->pending_n = n;
     e->pending_chunks = chunks;
+    CU(cudaEventRecord(e->ev_fwd, e->pipe[chunks - 1]));
     if (trace) {   // DSAC_TRACE=1: where one pass spends its time (last chunk's stream); forces the wait
         for (int c = 0; c < chunks; c++) CU(cudaStreamSynchronize(e->pipe[c]));
         float a = 0, b = 0, d = 0;
@@ -720,6 +774,7 @@ int dsac_forward(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coord
 int dsac_forward_dsac(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* coords, const int32_t* pix,
                       int32_t pix_shared, const double* gt_jp, int32_t random_draw, dsac_dsac_out* out) {
     if (!e || !out) return DSAC_ERR_ARG;
+    if (e->pending_chunks) return fail(e, DSAC_ERR_ARG, "dsac_forward_dsac: a submitted pass has not been awaited (dsac_forward_wait)");
     if (n < 1 || n > e->cfg.max_frames) return fail(e, DSAC_ERR_CAPACITY, "n_frames %d exceeds engine capacity %d", n, e->cfg.max_frames);
     if (!coords || !pix) return fail(e, DSAC_ERR_ARG, "null input");
     const dsac_config& c = e->cfg;
@@ -863,11 +918,13 @@ int dsac_forward_dsac(dsac_engine* e, int32_t n, int64_t frame0, const int16_t* 
 int dsac_backward(dsac_engine* e, int32_t n, const int16_t* coords, const int32_t* pix, int32_t pix_shared,
                   const double* gt_jp, dsac_backward_out* out) {
     if (!e || !out) return DSAC_ERR_ARG;
+    if (e->pending_chunks) return fail(e, DSAC_ERR_ARG, "dsac_backward: a submitted pass has not been awaited (dsac_forward_wait)");
     return backward_run(e, n, coords, pix, pix_shared, gt_jp, out);
 }
 
 int dsac_backward_dsac(dsac_engine* e, int32_t n, dsac_backward_dsac_out* out) {
     if (!e || !out) return DSAC_ERR_ARG;
+    if (e->pending_chunks) return fail(e, DSAC_ERR_ARG, "dsac_backward_dsac: a submitted pass has not been awaited (dsac_forward_wait)");
     return backward_dsac_run(e, n, out);
 }
 

@@ -331,23 +331,25 @@ DSAC_HD double filt_sqrt(double x) {   // x > 0
 // when the last step has not collapsed below 1e-9 of the problem's scale (near-double root, overflow, NaN) and
 // the caller must then treat the candidate as uncertain.
 DSAC_HD double cubic_first_root_seeded(double a2, double a1, double a0, bool* ok) {
+    // Branch-free: the lanes of a warp hold different candidates, and a divergent branch here costs every lane the
+    // instructions of both sides anyway.  Both closed forms are evaluated in fp32 (the fp32 pipe is idle in the filter)
+    // on arguments clamped into their domains, and the one that applies is selected.
     const double Q = (3 * a1 - a2 * a2) * (1.0 / 9), R = (9 * a2 * a1 - 27 * a0 - 2 * a2 * a2 * a2) * (1.0 / 54);
     const double Q3 = Q * Q * Q, D = Q3 + R * R, sh = a2 * (1.0 / 3);
     const float Qf = (float)Q, Rf = (float)R;
-    float s;
-    if (D <= 0) {
-        float cs = Rf * DSAC_RSQRTF_EARLY(-(float)Q3);
-        cs = fminf(1.f, fmaxf(-1.f, cs));
+    // D <= 0: three real roots, the largest one is 2 sqrt(-Q) cos(acos(R / sqrt(-Q^3)) / 3)
+    float cs = Rf * DSAC_RSQRTF_EARLY(fmaxf(-(float)Q3, 1e-37f));
+    cs = fminf(1.f, fmaxf(-1.f, cs));
 #if defined(__CUDA_ARCH__)
-        s = 2.f * sqrtf(-Qf) * __cosf(acosf(cs) * (1.f / 3));
+    const float s_trig = 2.f * sqrtf(fmaxf(-Qf, 0.f)) * __cosf(acosf(cs) * (1.f / 3));
 #else
-        s = 2.f * sqrtf(-Qf) * cosf(acosf(cs) * (1.f / 3));
+    const float s_trig = 2.f * sqrtf(fmaxf(-Qf, 0.f)) * cosf(acosf(cs) * (1.f / 3));
 #endif
-    } else {
-        float AD = cbrtf(fabsf(Rf) + sqrtf((float)D));
-        AD = (Rf >= 0) ? AD : -AD;
-        s = AD + ((AD == 0) ? 0.f : -Qf / AD);
-    }
+    // D > 0: one real root, Cardano
+    float AD = cbrtf(fabsf(Rf) + sqrtf(fmaxf((float)D, 0.f)));
+    AD = (Rf >= 0) ? AD : -AD;
+    const float s_card = AD + ((AD == 0) ? 0.f : -Qf / AD);
+    const float s = (D <= 0) ? s_trig : s_card;
     double y = (double)s - sh, dy = 0;
 #pragma unroll
     for (int it = 0; it < 3; it++) {
@@ -359,36 +361,34 @@ DSAC_HD double cubic_first_root_seeded(double a2, double a1, double a0, bool* ok
     return y;
 }
 
+// Real roots of the quartic by Ferrari's method, branch-free (see above): x[0..n) are the roots, n in {0, 2, 4}.
+// *uncertain: some sign decision lies within the 1e-9 band (then n = 0 and the caller flags the candidate).
 DSAC_HD int quartic_roots_banded(double a, double b, double c, double d, double e, double x[4], bool* uncertain) {
     const double TOL = 1e-9;
-    *uncertain = false;
-    double ia = filt_rcp(a);
+    const double ia = filt_rcp(a);
     b *= ia; c *= ia; d *= ia; e *= ia;
     bool cubic_ok;
-    double y1 = cubic_first_root_seeded(-c, d * b - 4 * e, 4 * c * e - d * d - b * b * e, &cubic_ok);
-    if (!cubic_ok) { *uncertain = true; return 0; }
-    double R2 = 0.25 * b * b - c + y1, mR = 0.25 * b * b + fabs(c) + fabs(y1);
-    if (!(fabs(R2) > TOL * mR)) { *uncertain = true; return 0; }   // also catches NaN and the R ~ 0 branch
-    if (R2 < 0) return 0;
-    double R = filt_sqrt(R2);
-    double u = 0.75 * b * b - 2 * c - R2;
-    double v = 0.25 * (4 * b * c - 8 * d - b * b * b) * filt_rcp(R);
-    double D2 = u + v, E2 = u - v, mD = fabs(0.75 * b * b) + fabs(2 * c) + R2 + fabs(v);
-    if (!(fabs(D2) > TOL * mD) || !(fabs(E2) > TOL * mD)) { *uncertain = true; return 0; }
-    int n = 0;
-    if (D2 > 0) {
-        double Dq = filt_sqrt(D2);
-        x[0] = 0.5 * R + 0.5 * Dq - 0.25 * b;
-        x[1] = x[0] - Dq;
-        n = 2;
-    }
-    if (E2 > 0) {
-        double Eq = filt_sqrt(E2);
-        x[n] = -0.5 * R + 0.5 * Eq - 0.25 * b;
-        x[n + 1] = x[n] - Eq;
-        n += 2;
-    }
-    return n;
+    const double y1 = cubic_first_root_seeded(-c, d * b - 4 * e, 4 * c * e - d * d - b * b * e, &cubic_ok);
+    const double R2 = 0.25 * b * b - c + y1, mR = 0.25 * b * b + fabs(c) + fabs(y1);
+    bool unc = !cubic_ok;
+    unc |= !(fabs(R2) > TOL * mR);                    // also catches NaN and the R ~ 0 branch of the closed form
+    const bool none = (R2 < 0);                       // no real root, by a margin no rounding can bridge
+    const double R2p = fabs(R2);
+    const double R = filt_sqrt(R2p);
+    const double u = 0.75 * b * b - 2 * c - R2p;
+    const double v = 0.25 * (4 * b * c - 8 * d - b * b * b) * filt_rcp(R);
+    const double D2 = u + v, E2 = u - v, mD = fabs(0.75 * b * b) + fabs(2 * c) + R2p + fabs(v);
+    unc |= (!(fabs(D2) > TOL * mD)) | (!(fabs(E2) > TOL * mD));
+    const bool hasD = D2 > 0, hasE = E2 > 0;
+    const double Dq = filt_sqrt(fabs(D2)), Eq = filt_sqrt(fabs(E2));
+    const double xd0 = 0.5 * R + 0.5 * Dq - 0.25 * b, xd1 = xd0 - Dq;
+    const double xe0 = -0.5 * R + 0.5 * Eq - 0.25 * b, xe1 = xe0 - Eq;
+    x[0] = hasD ? xd0 : xe0;
+    x[1] = hasD ? xd1 : xe1;
+    x[2] = xe0;
+    x[3] = xe1;
+    *uncertain = unc;
+    return (unc | none) ? 0 : ((hasD ? 2 : 0) + (hasE ? 2 : 0));
 }
 
 struct P3PProblem {
@@ -742,23 +742,32 @@ static long long g_filter_reason[24];
 #else
 #define DSAC_FLAG(k) true
 #endif
+#ifndef DSAC_FILTER_UNROLL
+#define DSAC_FILTER_UNROLL 1   /* root slots evaluated per trip of the filter's root loop (register pressure vs ILP) */
+#endif
 // Core of the filter on prepared inputs: unit bearings of points 0..2, the four scene coordinates and the pixel
 // (mu3, mv3) of the 4th point as P3P sees it (k_sample keeps 1/|(u, v, 1)| per cell in shared memory).
 DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], double mu3, double mv3, double f, double cx,
                             double cy, double thr) {
+    // BRANCH-FREE on purpose.  One thread filters one candidate, and the candidates of a warp differ in everything that a
+    // branch could test (number of real roots, sign of the roots, degeneracy): with early exits the warp ran at 16 of 32
+    // lanes (ncu, profiles/r02_*).  Every test below therefore only sets a flag; all four root slots are evaluated by
+    // all lanes (slots >= nroots are masked) and the verdict is the OR of the flags.  A NaN or infinity anywhere makes
+    // the comparison it reaches fail, and every comparison is written so that failing means "needs the full solve".
+    // Flag k <-> the early exit DSAC_FLAG(k) of the sequential formulation (kept for the host statistics build).
     const double ax = X[1][0] - X[0][0], ay = X[1][1] - X[0][1], az = X[1][2] - X[0][2];
     const double bx = X[2][0] - X[0][0], by = X[2][1] - X[0][1], bz = X[2][2] - X[0][2];
     const double gx = X[2][0] - X[1][0], gy = X[2][1] - X[1][1], gz = X[2][2] - X[1][2];
     const double s01 = ax * ax + ay * ay + az * az, s02 = bx * bx + by * by + bz * bz, s12 = gx * gx + gy * gy + gz * gz;
     const double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
     const double nn = nx * nx + ny * ny + nz * nz;
-    if (!(s01 > 0) || !(nn > 0)) return DSAC_FLAG(1);
+    bool flag = (!(s01 > 0)) | (!(nn > 0));                                              // (1) degenerate triangle
     const double p = 2 * (bear[1][0] * bear[2][0] + bear[1][1] * bear[2][1] + bear[1][2] * bear[2][2]);
     const double q = 2 * (bear[0][0] * bear[2][0] + bear[0][1] * bear[2][1] + bear[0][2] * bear[2][2]);
     const double r = 2 * (bear[0][0] * bear[1][0] + bear[0][1] * bear[1][1] + bear[0][2] * bear[1][2]);
     const double inv_c2 = filt_rcp(s01);
     const double a = inv_c2 * s12, b = inv_c2 * s02;
-    if (!(fabs(p * p + q * q + r * r - p * q * r - 1) > 1e-12)) return DSAC_FLAG(2);
+    flag |= !(fabs(p * p + q * q + r * r - p * q * r - 1) > 1e-12);                      // (2)
     const double N2 = 1 - a - b, N1 = q * (a - 1), N0 = 1 - a + b;
     const double D1 = b * r, D0 = -b * p;
     double xr[4];
@@ -771,12 +780,11 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         const double c2 = F2 * DD0 + F1 * DD1 + DD2 - b * (2 * N2 * N0 + N1 * N1) - br * (N1 * D0 + N0 * D1);
         const double c1 = F1 * DD0 + DD1 - b * (2 * N1 * N0) - br * (N0 * D0);
         const double c0 = DD0 - b * (N0 * N0);
-        if (!(fabs(c4) > 1e-12 * (fabs(c3) + fabs(c2) + fabs(c1) + fabs(c0)))) return DSAC_FLAG(3);
+        flag |= !(fabs(c4) > 1e-12 * (fabs(c3) + fabs(c2) + fabs(c1) + fabs(c0)));      // (3)
         bool uncertain;
         nroots = quartic_roots_banded(c4, c3, c2, c1, c0, xr, &uncertain);
-        if (uncertain) return DSAC_FLAG(4);
+        flag |= uncertain;                                                               // (4)
     }
-    if (nroots == 0) return false;   // no real root, by a margin no rounding can bridge
     // world triangle frame and the 4th point's coordinates in it
     const double inv_d = filt_rsqrt(s01), inv_n = filt_rsqrt(nn), d01 = s01 * inv_d;
     const double e1x = ax * inv_d, e1y = ay * inv_d, e1z = az * inv_d;
@@ -785,11 +793,12 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
     const double wx = X[3][0] - X[0][0], wy = X[3][1] - X[0][1], wz = X[3][2] - X[0][2];
     const double al = wx * e1x + wy * e1y + wz * e1z, be = wx * e2x + wy * e2y + wz * e2z, ga = wx * e3x + wy * e3y + wz * e3z;
     const double lim2 = (thr + DSAC_FILTER_BAND_PX) * (thr + DSAC_FILTER_BAND_PX);
+    constexpr int kRootUnroll = DSAC_FILTER_UNROLL;
+#pragma unroll kRootUnroll
     for (int i = 0; i < 4; i++) {
-        if (i >= nroots) break;
-        double x = xr[i];
+        double x = (i == 0) ? xr[0] : (i == 1) ? xr[1] : (i == 2) ? xr[2] : xr[3];
         const double Dn = D1 * x + D0;
-        if (!(fabs(Dn) > 1.1e-3 * (fabs(D1 * x) + fabs(D0)))) return DSAC_FLAG(5);   // (the full solve switches formula at 1e-3)
+        const bool f5 = !(fabs(Dn) > 1.1e-3 * (fabs(D1 * x) + fabs(D0)));   // (the full solve switches formula at 1e-3)
         double y = -((N2 * x + N1) * x + N0) * filt_rcp(Dn);
         const double f1 = (1 - a) * y * y - a * x * x - p * y + a * r * x * y + 1;
         const double f2 = (1 - b) * x * x - b * y * y - q * x + b * r * x * y + 1;
@@ -797,16 +806,16 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         const double j21 = 2 * (1 - b) * x - q + b * r * y, j22 = -2 * b * y + b * r * x;
         const double det = j11 * j22 - j12 * j21;
         const double jn = j11 * j11 + j12 * j12 + j21 * j21 + j22 * j22;
-        if (!(fabs(det) > 1e-4 * jn)) return DSAC_FLAG(6);
+        const bool f6 = !(fabs(det) > 1e-4 * jn);
         const double idet = filt_rcp(det);
         const double dx = (f1 * j22 - f2 * j12) * idet, dy = (j11 * f2 - j21 * f1) * idet;
         x -= dx;
         y -= dy;
-        if (!(fabs(dx) + fabs(dy) <= 1e-6 * (fabs(x) + fabs(y)))) return DSAC_FLAG(7);
-        if (x < -1e-6 || y < -1e-6) continue;
-        if (x < 1e-6 || y < 1e-6) return DSAC_FLAG(8);
+        const bool f7 = !(fabs(dx) + fabs(dy) <= 1e-6 * (fabs(x) + fabs(y)));
+        const bool neg = (x < -1e-6) | (y < -1e-6);        // certainly a non-physical solution: the root decides nothing
+        const bool f8 = (x < 1e-6) | (y < 1e-6);           // borderline positivity
         const double v = x * x + y * y - x * y * r;
-        if (!(v > 1e-12)) return DSAC_FLAG(9);
+        const bool f9 = !(v > 1e-12);
         const double Z = d01 * filt_rsqrt(v);
         const double L0 = x * Z, L1 = y * Z;
         const double M0x = L0 * bear[0][0], M0y = L0 * bear[0][1], M0z = L0 * bear[0][2];
@@ -821,9 +830,14 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         const double Z3 = M0z + al * c1z + be * c2z + ga * c3z;
         // |(cx + f X3 / Z3 - mu3, cy + f Y3 / Z3 - mv3)|^2 > lim2, multiplied through by Z3^2 (no division)
         const double gu = f * X3 - (mu3 - cx) * Z3, gv = f * Y3 - (mv3 - cy) * Z3, zz = Z3 * Z3;
-        if (!(gu * gu + gv * gv > lim2 * zz) || !(zz > 0)) return DSAC_FLAG(10);
+        const bool f10 = (!(gu * gu + gv * gv > lim2 * zz)) | (!(zz > 0));
+        const bool root_flag = f5 | f6 | f7 | ((!neg) & (f8 | f9 | f10));
+#if defined(DSAC_FILTER_STATS) && !defined(__CUDA_ARCH__)
+        if (!flag && i < nroots && root_flag) g_filter_reason[f5 ? 5 : f6 ? 6 : f7 ? 7 : f8 ? 8 : f9 ? 9 : 10]++;
+#endif
+        flag |= (i < nroots) & root_flag;
     }
-    return false;
+    return flag;
 }
 
 DSAC_HD bool p3p_quick_inline(const P3PProblem& pr, double f, double cx, double cy, double inv_f, double thr) {

@@ -571,10 +571,13 @@ __global__ void __launch_bounds__(K1F_THREADS, K1F_MIN_BLOCKS) k1_filter(K1Split
 // ------------------------------------------------------------------ k1_solve
 // Full fp64 P3P + the reference's reprojection check (cnn_softam.h:1041-1059) on the flagged candidates; 4 lanes per
 // candidate, lane `sub` handles quartic root `sub` (as phase D of k_sample).
+#ifndef K1V_GROUP
+#define K1V_GROUP 4   /* lanes per flagged candidate: 4 = one quartic root per lane, 2 = two roots per lane, 1 = one thread per candidate */
+#endif
 __global__ void __launch_bounds__(K1V_THREADS) k1_solve(K1SplitParams q) {
     const SampleParams& p = q.sp;
     const int tid = threadIdx.x;
-    constexpr int GROUP = 4, GROUPS = K1V_THREADS / GROUP;
+    constexpr int GROUP = K1V_GROUP, GROUPS = K1V_THREADS / GROUP, ROOTS = 4 / GROUP;
     const int n_q = q.fq_n[q.round];
     const int sub = tid % GROUP;
     for (int base = blockIdx.x * GROUPS; base < n_q; base += gridDim.x * GROUPS) {
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(K1V_THREADS) k1_solve(K1SplitParams q) {
             }
             P3PFront fr;
             p3p_front(pr, p.f, p.cx, p.cy, fr);
-            nsol = p3p_full(pr, fr, p.f, p.cx, p.cy, R, t, &e2, sub, sub + 1);
+            nsol = p3p_full(pr, fr, p.f, p.cx, p.cy, R, t, &e2, sub * ROOTS, (sub + 1) * ROOTS);
             if (nsol == 0) e2 = 1.7976931348623157e308;
         }
         // minimum over the group; ties go to the lower root index, as the sequential loop would

@@ -20,7 +20,7 @@ ST_SAMPLER_EXHAUSTED, ST_REFINE_ABORTED = 1, 2
 EXPORTS = [
     "dsac_default_config", "dsac_engine_create", "dsac_engine_destroy", "dsac_last_error", "dsac_engine_config",
     "dsac_forward", "dsac_forward_submit", "dsac_forward_wait", "dsac_forward_device", "dsac_fetch", "dsac_device_view_get", "dsac_set_stages",
-    "dsac_set_tail_split", "dsac_launch_count", "dsac_set_score_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_gather_patches_device", "dsac_coords_from_prediction_device", "dsac_kabsch",
+    "dsac_set_tail_split", "dsac_launch_count", "dsac_set_score_hook", "dsac_set_score_backward_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_gather_patches_device", "dsac_coords_from_prediction_device", "dsac_kabsch",
     "dsac_stochastic_subsample",
     "dsac_synth_frames", "dsac_version",
 ]
@@ -66,6 +66,7 @@ class DsacOut(C.Structure):
 
 
 SCORE_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
+SCORE_BACKWARD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
 
 _lib = None
 
@@ -107,6 +108,7 @@ def load(build_if_missing=True):
     lib.dsac_set_stages.argtypes = [C.c_void_p, C.c_uint32]
     lib.dsac_set_tail_split.argtypes = [C.c_void_p, C.c_int32]
     lib.dsac_set_score_hook.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dsac_set_score_backward_hook.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dsac_backward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.POINTER(BackwardOut)]
     lib.dsac_forward_dsac.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
@@ -329,6 +331,20 @@ class Engine:
 
         self._hook = SCORE_HOOK(tramp)
         self._check(self.lib.dsac_set_score_hook(self.h, C.cast(self._hook, C.c_void_p), None))
+
+    def set_score_backward_hook(self, fn):
+        """fn(d_diffmaps:int, d_score_grads:int, n:int, H:int, d_diffmap_grads:int, stream:int) -> int (device pointers):
+        the seam's adjoint (lua_calls.h:312-341); must be registered together with the forward hook."""
+        if fn is None:
+            self._bw_hook = None
+            self._check(self.lib.dsac_set_score_backward_hook(self.h, None, None))
+            return
+
+        def tramp(dm, sg, n, H, out, stream, user):
+            return int(fn(dm or 0, sg or 0, n, H, out or 0, stream or 0))
+
+        self._bw_hook = SCORE_BACKWARD_HOOK(tramp)
+        self._check(self.lib.dsac_set_score_backward_hook(self.h, C.cast(self._bw_hook, C.c_void_p), None))
 
     def forward_dsac(self, coords, pix, gt_jp, random_draw=True, frame0=0, want_inlier_maps=False):
         """dsac_forward_dsac: the DSAC / RANSAC variant (draw + refine all hypotheses + expected loss)."""

@@ -168,6 +168,17 @@ typedef int (*dsac_score_hook)(const float* d_diffmaps, int32_t n_frames, int32_
                                void* stream, void* user);
 int dsac_set_score_hook(dsac_engine* e, dsac_score_hook fn, void* user);
 
+/* The seam's adjoint: replaces backward(maps, stateObj, scoreOutputGradients, gradients) (lua_calls.h:312-341; call site
+ * cnn_softam.h:607 in dScore, cnn.h:672 in dSMScore).  Called by dsac_backward / dsac_backward_dsac with DEVICE pointers:
+ * the diffmaps of the preceding forward [n][H][N], the score output-gradients [n][H] already clamped to +-grad_clamp
+ * (the clamp of train_score_softam.lua:97), and the buffer to fill: diffmap_grads [n][H][40][40] doubles, element (y, x) =
+ * d score_h / d diffmap_h(y, x) -- what the reference holds in gradients[c](y, x) after lua_calls.h:326-338.
+ * A forward hook and a backward hook must be registered together: with only one of them set the backward entry points
+ * return DSAC_ERR_ARG (they would otherwise differentiate a score the forward did not compute). */
+typedef int (*dsac_score_backward_hook)(const float* d_diffmaps, const double* d_score_grads, int32_t n_frames, int32_t n_hyps,
+                                        double* d_diffmap_grads, void* stream, void* user);
+int dsac_set_score_backward_hook(dsac_engine* e, dsac_score_backward_hook fn, void* user);
+
 /* Backward of one training round (train_ransac_softam.cpp:288-394) for the n frames of the
  * preceding dsac_forward call: dLoss/dY, [n][N][3] doubles, row p = y*40+x
  * (what the driver hands to the coordinate-CNN backward, train_ransac_softam.cpp:412).

@@ -413,12 +413,48 @@ def backward_dsac(cfg, coords, pix, gt_R, gt_t, fwd):
     return out
 
 
-def bench_forward(cfg, coords, pix, n_threads=1, with_refine=False, want_avg=False):
+_variants = {}
+
+
+def variant_lib(variant):
+    """A differently COMPILED build of the same oracle sources, for the CPU timing arm only (bench.py): "parity" = the -O2
+    -ffp-contract=off library the tests use; "perf" = -O3 -march=x86-64-v3 -fopenmp; "native" / "ofast" = -O3 / -Ofast
+    -march=native, built on the calling box.  Returns (CDLL, flags description) or (None, why)."""
+    if variant == "parity":
+        return lib(), "-O2 -ffp-contract=off (parity build)"
+    if variant in _variants:
+        return _variants[variant]
+    target = {"perf": "libdsac_oracle_perf.so", "native": "libdsac_oracle_native.so", "ofast": "libdsac_oracle_ofast.so"}[variant]
+    flags = {"perf": "-O3 -march=x86-64-v3 -fopenmp", "native": "-O3 -march=native -fopenmp", "ofast": "-Ofast -march=native -fopenmp"}[variant]
+    path = os.path.join(_HERE, target)
+    try:
+        if variant != "perf" or not os.path.exists(path):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if variant != "perf" else "-s", target], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+        l = C.CDLL(path)
+        l.orc_bench_forward.restype = C.c_double
+        _variants[variant] = (l, flags)
+    except Exception as e:   # no compiler on this box, or an instruction set this CPU lacks
+        _variants[variant] = (None, "unavailable: %s" % e)
+    return _variants[variant]
+
+
+def bench_forward(cfg, coords, pix, n_threads=1, with_refine=False, want_avg=False, variant="parity", stages=None):
+    """Wall-clock seconds of orc_forward over the frames with n_threads host threads (frames in parallel).
+    stages: a list that receives the per-stage seconds summed over threads [sampling, scoring, averaging, refinement]."""
     coords = np.ascontiguousarray(coords, np.int16).reshape(-1, N, 3)
     pix = np.ascontiguousarray(pix, np.int32).reshape(-1, N, 2)
     nf = coords.shape[0]
     avg = np.zeros((nf, 6)) if want_avg else None
-    secs = lib().orc_bench_forward(C.byref(cfg), nf, _p(coords), _p(pix), int(n_threads), int(with_refine), _p(avg))
+    l, _ = variant_lib(variant)
+    if l is None:
+        raise RuntimeError("oracle build %r is not available" % variant)
+    four = (C.c_double * 4)()
+    l.orc_stage_seconds(four, 1)
+    secs = l.orc_bench_forward(C.byref(cfg), nf, _p(coords), _p(pix), int(n_threads), int(with_refine), _p(avg))
+    l.orc_stage_seconds(four, 1)
+    if stages is not None:
+        stages[:] = list(four)
     return (secs, avg) if want_avg else secs
 
 

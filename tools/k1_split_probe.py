@@ -71,7 +71,7 @@ def timeit(nf):
     d_coords = torch.from_numpy(coords).cuda(); d_pix = torch.from_numpy(pix).cuda(); d_gt = torch.from_numpy(gt_jp).cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    for mode in ("mono", "split"):
+    for mode in (("split",) if os.environ.get("SPLIT_ONLY") else ("mono", "split")):
         eng = make(mode, max_frames=nf)
         for stages, name in ((E.STAGE_SAMPLE, "sampler"), (E.STAGE_ALL, "step")):
             eng.set_stages(stages)
