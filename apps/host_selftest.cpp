@@ -6,12 +6,23 @@
 #include <iostream>
 
 #include "../dsac_b200/host/cnn_softam.h"
+#include "../dsac_b200/host/read_data.h"
 #include "../dsac_b200/host/thread_rand.h"
 
 using namespace cvlite;
 #define CHECK(c) do { if (!(c)) { std::printf("FAILED %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 
 int main(int argc, const char* argv[]) {
+    // `host_selftest pose <file>`: the ground-truth pose of a 7-Scenes pose file (read_data.cpp:69-133 + Hypothesis(info)),
+    // printed with 17 digits for tests/test_oracle_vs_ref.py (translation.txt is looked up in the current directory)
+    if (argc == 3 && std::string(argv[1]) == "pose") {
+        jp::info_t info;
+        if (!jp::readData(argv[2], info)) { std::printf("cannot read %s\n", argv[2]); return 1; }
+        Hypothesis h(info);
+        for (int i = 0; i < 9; i++) std::printf("%.17g ", h.getRotation()(i / 3, i % 3));
+        std::printf("%.17g %.17g %.17g\n", h.getTranslation().x, h.getTranslation().y, h.getTranslation().z);
+        return 0;
+    }
     // Hypothesis: Rodrigues 6-vector round trip, inverse, composition, angular distance
     Hypothesis h(std::vector<double>{0.3, -0.2, 0.5, 100, -50, 2000});
     std::vector<double> v = h.getRodVecAndTrans();

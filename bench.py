@@ -29,6 +29,16 @@ FRAMES_PER_GPU = 1024
 BYTES_F = NPTS * (6 + 8) + H * (48 + 8) + 56           # fused, scores only   
 BYTES_M = BYTES_F + H * NPTS * 4                       # diffmap materialised (reference behaviour)
 FLOPS_PER_PAIR = 38
+# fp64 flop model of the sampler's conservative filter (one thread per candidate; DESIGN.md section 5, counted from
+# p3p_quick_core / quartic_roots_banded in pose_math.cuh with FMA = 2 flops, a Newton-refined reciprocal = 8, rsqrt = 11):
+#   set-up (triangle, quadrics, quartic coefficients, Ferrari + cubic Newton, world frame) ... 388 flops
+#   one root slot (Newton step on the two quadrics, positivity, 4th point by congruence) ..... 173 flops
+# ALGORITHMIC work = set-up + the REAL roots of the quartic: 96.9 % of the candidates have two, 0.7 % four, 2.4 % none
+# (tools/filter_stats.py over 2 * 10^6 candidates of the benchmark frames) -> 1.97 root slots = 729 flops per candidate.
+# The kernel evaluates slots 0 and 1 in every lane and slots 2, 3 only in warps that hold a four-root candidate (one in
+# five): ~2.4 slots = 803 executed flops per candidate.
+FILTER_FLOPS_SETUP, FILTER_FLOPS_ROOT, FILTER_MEAN_ROOTS, FILTER_EXEC_SLOTS = 388, 173, 1.97, 2.4
+FP64_PEAK_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12       # 148 SMs x 64 FMA/clk x 2 x 1.965 GHz = 37.2 (B200 non-tensor fp64)
 
 
 def parse():
@@ -123,38 +133,78 @@ def cpu_model():
     return "unknown"
 
 
-def run_cpu_sample(n_frames, threads, frame0=0):
-    """The oracle (CPU restatement of the reference path) on `n_frames` frames of the SAME workload."""
-    import dsac_b200.engine as E
+def run_cpu_sample(n_frames, threads, frame0=0, variant="perf", stages=None):
+    """The oracle (CPU restatement of the reference path) on `n_frames` frames of the SAME workload.  Inputs come from the
+    host-only generator library (dsac_b200/libdsac_synth.so: no CUDA library is mapped by this leg)."""
+    from dsac_b200 import synth
     from oracle import oracle as O
-    coords, pix, _, _ = E.synth_frames(n_frames, frame0=frame0)
+    coords, pix, _, _ = synth.synth_frames(n_frames, frame0=frame0)
     cfg = O.default_config(seed=1305 + frame0)
-    secs = O.bench_forward(cfg, coords, pix, n_threads=threads, with_refine=True)
+    secs = O.bench_forward(cfg, coords, pix, n_threads=threads, with_refine=True, variant=variant, stages=stages)
     return n_frames * H / secs, secs
 
 
+def pick_cpu_variant():
+    """-O3 -march=native build made on THIS box if a compiler is here, else the shipped -O3 -march=x86-64-v3 build."""
+    from oracle import oracle as O
+    for v in ("native", "perf", "parity"):
+        lib, flags = O.variant_lib(v)
+        if lib is not None:
+            return v, flags
+    raise SystemExit("no oracle library available")
+
+
+def cpu_report(threads, n_frames, frame0=0):
+    """CPU baseline per BASELINE.md section 3: perf build, 1 thread and all threads, per-stage split at the reference's
+    print points (cnn_softam.h:1062, 1074, 1096, 1156), plus the reference's own -Ofast for information."""
+    from oracle import oracle as O
+    variant, flags = pick_cpu_variant()
+    run_cpu_sample(min(n_frames, threads), threads, variant=variant)             # page in, spin the cores up
+    st = []
+    v_all, secs = run_cpu_sample(n_frames, threads, frame0=frame0, variant=variant, stages=st)
+    tot = sum(st) or 1.0
+    n1 = max(8, n_frames // max(1, threads))
+    v_one, secs1 = run_cpu_sample(n1, 1, frame0=frame0, variant=variant)
+    out = {"value": v_all, "unit": "hyp/s", "cores": threads, "kind": "port", "build": flags,
+           "sample": "%d frames x %d hyp x 1600 pts of the same batch, full pipeline (sample+score+softargmax+refine), %.2f s wall" % (n_frames, H, secs),
+           "one_thread": {"value": v_one, "frames": n1, "seconds": secs1},
+           "stage_share": {"sampling": st[0] / tot, "scoring": st[1] / tot, "averaging": st[2] / tot, "refinement": st[3] / tot},
+           "cpu": cpu_model(),
+           "note": "oracle = CPU restatement of the reference path with the closed-form score, pinned to the reference's own code "
+                   "(tests/test_oracle_vs_ref.py); it omits the reference's Lua/cuDNN round trip, i.e. a lower bound on the reference's CPU time"}
+    lib, oflags = O.variant_lib("ofast")
+    if lib is not None:
+        run_cpu_sample(min(n_frames, threads), threads, variant="ofast")
+        v_fast, _ = run_cpu_sample(n_frames, threads, frame0=frame0, variant="ofast")
+        out["ofast"] = {"value": v_fast, "build": oflags + " (the reference's own flag, core/CMakeLists.txt:7; informational)"}
+    return out
+
+
 def reference_arm(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be
-    built here (OpenCV C++/Lua/Torch7/png++ missing), so this is the oracle port on all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be linked against its
+    real dependencies here (OpenCV C++/Lua/Torch7/png++ missing; oracle/_ref compiles it against shims for PINNING only),
+    so this arm times the oracle port -- built for speed -- on all host threads.  It maps no CUDA library."""
     if rank != 0:
         return
     threads = cpu_threads()
-    per_step = max(threads * 2, 64)
-    for _ in range(args.warmup):
-        run_cpu_sample(max(threads, 16), threads)
+    variant, flags = pick_cpu_variant()
+    per_step = max(threads * 4, 64)
+    for _ in range(max(1, args.warmup)):
+        run_cpu_sample(max(threads, 16), threads, variant=variant)
     t = 0.0
     for s in range(args.steps):
-        _, secs = run_cpu_sample(per_step, threads, frame0=s * per_step)
+        _, secs = run_cpu_sample(per_step, threads, frame0=s * per_step, variant=variant)
         t += secs
     value = per_step * H * args.steps / t
-    sample = "%d frames/step x %d hyp x 1600 pts (same generator, seeds and config as the GPU arm), %d threads" % (per_step, H, threads)
+    sample = "%d frames/step x %d hyp x 1600 pts (same generator, seeds and config as the GPU arm, whose step is %d frames: " \
+             "throughput-normalised), %d threads, build %s" % (per_step, H, FRAMES_PER_GPU, threads, flags)
     line = {
         "impl": "reference", "metric": "hypotheses scored/sec (256 hyp x 1600 pts/img)", "value": value, "unit": "hyp/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config4-shaped batch, CPU sample: " + sample, "n_hyps": H, "points": NPTS,
+        "config": {"workload": "config4-shaped batch, CPU sample: " + sample, "n_hyps": H, "points": NPTS, "frames_per_step": per_step,
                    "stages": "sample+score+softargmax+refine+eval"},
-        "cpu_baseline": {"value": value, "unit": "hyp/s", "cores": threads, "kind": "port", "sample": sample, "cpu": cpu_model()},
+        "cpu_baseline": {"value": value, "unit": "hyp/s", "cores": threads, "kind": "port", "sample": sample, "cpu": cpu_model(), "build": flags},
         "e2e": {"value": value, "unit": "hyp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -302,20 +352,28 @@ def main():
     e2e_sync_value = n_total * H * args.steps / float(t[1].item())
     clk = clocks.stop() if clocks else None
 
-    # ---- per-stage kernel durations (stage-isolated launches, CUDA events) and the K2 roofline
+    # ---- per-stage durations (stage-isolated launches, CUDA events), the sampler's per-kernel split and the rooflines
     stage_ms = {}
-    eng.set_tail_split(0)      # one launch per stage over the whole batch (the timed steps above ran with the tail split on)
-    for name, mask in (("k_sample", E.STAGE_SAMPLE), ("k_score", E.STAGE_SCORE), ("k_refine", E.STAGE_REFINE | E.STAGE_EVAL)):
+    reps_s = max(3, min(args.steps, 10))
+    for name, mask in (("sampler", E.STAGE_SAMPLE), ("k_score", E.STAGE_SCORE), ("k_refine", E.STAGE_REFINE | E.STAGE_EVAL)):
         eng.set_stages(E.STAGE_ALL)
         step_device()
         eng.set_stages(mask)
         step_device()
         torch.cuda.synchronize()
-        stage_ms[name] = timed_steps(step_device, max(3, min(args.steps, 10))) / max(3, min(args.steps, 10))
+        stage_ms[name] = timed_steps(step_device, reps_s) / reps_s
+    # the sampler's kernels, from CUDA events the engine records between its launches (dsac_sampler_profile)
+    eng.set_stages(E.STAGE_SAMPLE)
+    eng.sampler_profile(True)
+    k1_ms, k1_cnt = [0.0] * 4, [0] * 4
+    for _ in range(reps_s):
+        flush.zero_()
+        step_device()
+        ms_k, cnt_k = eng.sampler_profile_read()
+        k1_ms = [a + b / reps_s for a, b in zip(k1_ms, ms_k)]
+        k1_cnt = cnt_k
+    eng.sampler_profile(False)
     eng.set_stages(E.STAGE_ALL)
-    step_device(); torch.cuda.synchronize()
-    serial_ms = timed_steps(step_device, max(3, min(args.steps, 10))) / max(3, min(args.steps, 10))   # whole step, tail split off
-    eng.set_tail_split(1)
     peak, peak_src = peaks()
     k2_s = stage_ms["k_score"] * 1e-3
     achieved = BYTES_M * nf / k2_s / 1e9
@@ -327,21 +385,54 @@ def main():
         except Exception:
             traffic = None
     ssum = sum(stage_ms.values())
+    kernels_ms = {"k1_cells+k1_slot (MT19937 streams, candidate boundaries, ordered selection)": k1_ms[0],
+                  "k1_filter (conservative fp64 P3P filter, 1 thread per candidate)": k1_ms[1],
+                  "k1_solve (full fp64 P3P + reprojection check on the flagged)": k1_ms[2],
+                  "k_sample resume tail (streams the rounds left unfinished; normally empty)": k1_ms[3],
+                  "k_score": stage_ms["k_score"], "k_refine": stage_ms["k_refine"]}
+    # dominant kernel: the sampler's filter.  Point-wise fp64 arithmetic on shared-memory-resident data: neither HBM nor
+    # tensor cores bound it, the fp64 pipe does -- reported against the chip's non-tensor fp64 peak.
+    filt_s = max(k1_ms[1], 1e-9) * 1e-3
+    flops_alg = (FILTER_FLOPS_SETUP + FILTER_MEAN_ROOTS * FILTER_FLOPS_ROOT) * k1_cnt[0]
+    flops_exec = (FILTER_FLOPS_SETUP + FILTER_EXEC_SLOTS * FILTER_FLOPS_ROOT) * k1_cnt[0]
+    roofline = {"kernel": "k1_filter (dominant: %.0f %% of the stage-isolated step) -- conservative fp64 P3P filter over every sampled minimal set" % (100 * k1_ms[1] / ssum),
+                "bound": "fp64 pipe (not hbm / tensor: point-wise fp64 arithmetic on data staged in shared memory; see roofline_hbm for the HBM-bound kernel)",
+                "achieved": flops_alg / filt_s / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": flops_alg / filt_s / 1e12 / FP64_PEAK_TFLOPS,
+                "traffic": None, "peak_source": "148 SMs x 64 fp64 FMA/clk x 2 x 1.965 GHz (no measured fp64 peak in MEASURED_PEAKS.json)",
+                "algorithmic_flops_per_candidate": FILTER_FLOPS_SETUP + FILTER_MEAN_ROOTS * FILTER_FLOPS_ROOT,
+                "executed_flops_per_candidate": FILTER_FLOPS_SETUP + FILTER_EXEC_SLOTS * FILTER_FLOPS_ROOT, "executed_frac": flops_exec / filt_s / 1e12 / FP64_PEAK_TFLOPS,
+                "candidates_per_launch_set": k1_cnt[0], "ms_per_step": k1_ms[1], "share_of_step": k1_ms[1] / ssum}
+    roofline_hbm = {"kernel": "k_score<write_diffmaps=1> (HxN reprojection-error matrix + soft-inlier score + soft-argmax tail)",
+                    "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_M * nf,
+                    "ms_per_launch": stage_ms["k_score"], "share_of_step": stage_ms["k_score"] / ssum,
+                    "fp32_gflops": FLOPS_PER_PAIR * H * NPTS * nf / k2_s / 1e9,
+                    "step_level": {"achieved": BYTES_M * nf / (ms_total / args.steps * 1e-3) / 1e9, "frac": BYTES_M * nf / (ms_total / args.steps * 1e-3) / 1e9 / peak,
+                                   "note": "algorithmic bytes of the whole step (mode M) over the whole step's time"}}
 
-    def ncu_value(fname, key):
-        """A metric of the committed ncu summary of this round's kernel (profiles/, static evidence; None if absent)."""
-        try:
-            for line in open(os.path.join(ROOT, "profiles", fname)):
-                if line.strip().startswith(key + " "):
-                    return float(line.split()[1])
-        except Exception:
-            pass
-        return None
-    roofline = {"kernel": "k_score<write_diffmaps=1> (HxN reprojection-error matrix + soft-inlier score + soft-argmax tail)",
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_M * nf,
-                "ms_per_launch": stage_ms["k_score"], "share_of_step": stage_ms["k_score"] / ssum,
-                "fp32_gflops": FLOPS_PER_PAIR * H * NPTS * nf / k2_s / 1e9}
+    # ---- BASELINE config 4 verbatim (strong scaling): the SAME 1024 frames split over the ranks, 1024 / N per GPU
+    strong = None
+    nf_s = FRAMES_PER_GPU // world
+    if world > 1 and nf_s >= 1:
+        lo_s = rank * nf_s
+
+        def step_strong():
+            eng.forward_device(nf_s, d_coords.data_ptr(), d_pix.data_ptr(), 0, d_gt.data_ptr(), lo_s, stream)
+        for _ in range(3):
+            step_strong()
+        barrier()
+        ms_s = timed_steps(step_strong, args.steps)
+        barrier()
+        ts = torch.tensor([ms_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_s = float(ts.item())
+        strong = {"workload": "BASELINE config 4 as written: %d frames in total, %d per GPU" % (nf_s * world, nf_s), "frames_total": nf_s * world,
+                  "frames_per_gpu": nf_s, "ms_per_step": ms_s / args.steps, "value": nf_s * world * H * args.steps / (ms_s * 1e-3), "unit": "hyp/s",
+                  "note": "strong scaling: per-GPU work shrinks with N, so launch latency and the sampler's round structure (a fixed "
+                          "number of dependent kernel launches per pass) weigh more than in the weak-scaling `value`"}
+    elif world == 1:
+        strong = {"workload": "BASELINE config 4 as written: 1024 frames on one GPU (identical to `value`)", "frames_total": nf, "frames_per_gpu": nf,
+                  "ms_per_step": ms_total / args.steps, "value": value, "unit": "hyp/s"}
 
     # ---- config 2: single frame latency (1 frame, 256 hyp, forward scoring + soft-argmax)
     single = None
@@ -447,16 +538,32 @@ def main():
         engu.close()
         del patches, fr
 
+    # ---- BASELINE config 5: the 1000-frame 7Scenes-shaped sequence through the C++ test driver (its own engines, one host
+    #      thread per GPU; the other ranks idle meanwhile)
+    sequence = None
+    barrier()
+    if rank == 0:
+        try:
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "apps"), "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            with tempfile.TemporaryDirectory() as d:
+                cmd = [os.path.join(ROOT, "apps", "test_ransac_softam"), "-frames", "1000", "-batch", "250", "-gpus", str(world)]
+                subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=300)   # first run: engine creation, page-in
+                o = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=300)
+                summ = [float(x) for x in open(os.path.join(d, "ransac_test_loss_obj_model_init.net_rdraw1_softam.txt")).read().split()]
+                tail = o.stdout.strip().splitlines()[-1]
+                fps = float(tail.split(" s: ")[1].split(" frames/s")[0])
+                sequence = {"workload": "config 5: 1000-frame synthetic chess-shaped trajectory, apps/test_ransac_softam -gpus %d (host buffers, "
+                                        "log files written), scores only (no diffmap materialisation)" % world,
+                            "frames_per_s": fps, "hyp_per_s": fps * H, "accuracy_5cm5deg": summ[0], "median_rot_deg": summ[5], "median_t_mm": summ[6]}
+        except Exception as ex:   # the driver is an extra: never lose the bench line over it
+            sequence = {"error": str(ex)[:200]}
+    barrier()
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
     cpu = None
     if rank == 0 and world == 1:
         threads = cpu_threads()
-        ncpu = args.cpu_frames or max(256, 2 * threads)
-        run_cpu_sample(min(ncpu, threads), threads)       # warm the library / page in
-        v, secs = run_cpu_sample(ncpu, threads)
-        cpu = {"value": v, "unit": "hyp/s", "cores": threads, "kind": "port",
-               "sample": "first %d of the %d frames x %d hyp x 1600 pts, full pipeline, %.2f s wall (%.1f s CPU)" % (ncpu, nf, H, secs, secs * min(threads, ncpu)),
-               "cpu": cpu_model(), "note": "oracle = CPU restatement with closed-form score; omits the reference's Lua/cuDNN round trip"}
+        cpu = cpu_report(threads, args.cpu_frames or max(256, 4 * threads), frame0=frame0)
 
     if rank == 0:
         line = {
@@ -469,8 +576,7 @@ def main():
                        "frames_per_gpu": nf, "n_hyps": H, "points": NPTS, "streams_per_frame": 1, "inlier_ratio": 0.5,
                        "noise_mm": 25.0, "data_seed": 20170721, "sampler_seed": 1305, "alpha": 0.1, "beta": 0.5,
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world,
-                       "tail_split": "on (dsac_set_tail_split 1): the frames of the sampler's last, partial wave run on the caller's stream, the "
-                                     "whole waves on a high-priority side stream; %.3f ms/step with it off" % serial_ms,
+                       "sampler": "round-based pipeline of flat kernels (sampler_split.cuh), %d launches per pass" % (gpu_launches // max(1, args.steps)),
                        "l2": "256 MB buffer written between timed steps (flush); each step also streams %.2f GB of diffmaps" % (BYTES_M * nf / 1e9)},
             "e2e": {"value": e2e_value, "unit": "hyp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(t[0].item()) / args.steps,
@@ -484,17 +590,16 @@ def main():
                                   "api": "one blocking dsac_forward per step (H2D, kernels, D2H strictly serial)"}},
             "gpu_launches": gpu_launches,
             "roofline": roofline,
-            "kernels_ms": stage_ms,
-            "sampler": {"kernel": "k_sample (%.0f %% of the stage-isolated step; fp64-latency / barrier-bound, no HBM or tensor roofline applies: "
-                                  "see profiles/r01_k_sample_full.txt)" % (100 * stage_ms["k_sample"] / ssum),
-                        "candidates_per_s": quality["candidates_per_frame"] * nf / (stage_ms["k_sample"] * 1e-3),
+            "roofline_hbm": roofline_hbm,
+            "stages_ms": stage_ms,
+            "kernels_ms": kernels_ms,
+            "sampler": {"ms_per_step": stage_ms["sampler"], "share_of_step": stage_ms["sampler"] / ssum,
+                        "candidates_per_s": k1_cnt[0] / (stage_ms["sampler"] * 1e-3),
                         "candidates_per_accepted_hypothesis": quality["candidates_per_frame"] / H,
-                        "ms_per_launch": stage_ms["k_sample"],
-                        "ncu": {"source": "profiles/r01_k_sample_full.txt (one launch under ncu --set full)",
-                                "fp64_pipe_pct": ncu_value("r01_k_sample_full.txt", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
-                                "issue_active_pct": ncu_value("r01_k_sample_full.txt", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                                "barrier_stalls_per_issue": ncu_value("r01_k_sample_full.txt", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
-                                "dram_pct": ncu_value("r01_k_sample_full.txt", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}},
+                        "generated_over_consumed": k1_cnt[0] / max(1.0, quality["candidates_per_frame"] * nf),
+                        "flagged_by_filter": k1_cnt[1], "accepted": k1_cnt[2], "rounds_with_work": k1_cnt[3]},
+            "strong_scaling": strong,
+            "sequence": sequence,
             "cpu_baseline": cpu,
             "single_frame": single,
             "train_round": train,

@@ -33,6 +33,21 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the CUDA engine cannot be built (there is no CPU fallback)")
 
 
+SYNTH_LIB = os.path.join(HERE, "libdsac_synth.so")
+
+
+def build_synth(force=False):
+    """Host-only build (g++) of host_util.cpp: the synthetic-frame generator and stochasticSubSample without any CUDA
+    dependency, so that CPU-only consumers (bench.py --impl reference) do not have to map the CUDA library."""
+    src = os.path.join(CSRC, "host_util.cpp")
+    deps = [src, os.path.join(CSRC, "pose_math.cuh"), os.path.join(HERE, "..", "include", "dsac_b200.h")]
+    if not force and os.path.exists(SYNTH_LIB) and all(os.path.getmtime(SYNTH_LIB) >= os.path.getmtime(d) for d in deps):
+        return SYNTH_LIB
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SYNTH_LIB, src])
+    return SYNTH_LIB
+
+
 def _deps():
     out = [os.path.join(HERE, "..", "include", "dsac_b200.h"), os.path.abspath(__file__)]
     for f in os.listdir(CSRC):
@@ -48,8 +63,13 @@ def needs_build():
 
 
 def build(force=False, verbose=False, out=None, csrc=None):
-    """out / csrc: build a variant of the library somewhere else (tools/sweep.py); the product is LIB from CSRC."""
+    """out / csrc: build a variant of the library somewhere else (tools/sweep.py); the product is LIB from CSRC.
+    DSAC_SKIP_BUILD=1: use the library as it is (a snapshot sent to the GPU box must not be rebuilt from sources that were
+    being edited while the job waited in the queue)."""
+    if out is None and not force and os.environ.get("DSAC_SKIP_BUILD") and os.path.exists(LIB):
+        return LIB
     if out is None and not force and not needs_build():
+        build_synth()
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + \
         [os.path.join(csrc or CSRC, s) for s in SOURCES]
@@ -60,6 +80,8 @@ def build(force=False, verbose=False, out=None, csrc=None):
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libdsac_b200.so")
+    if out is None:
+        build_synth(force)
     return out or LIB
 
 

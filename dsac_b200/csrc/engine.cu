@@ -98,7 +98,7 @@ struct dsac_engine {
     int tail_split = 1;
     // split sampler (sampler_split.cuh): per-stream state and round buffers, sized at creation
     int k1_mode = 1;                // 1: round-based pipeline of flat kernels; 0: monolithic k_sample (DSAC_K1_MODE=mono)
-    int k1_rounds = 6, k1_cap = 0;
+    int k1_rounds = 4, k1_cap = 0;
     int k1_filter_grid = 0, k1_solve_grid = 0;
     unsigned long long k1_calls = 0;
     K1SlotState* d_k1_state = nullptr;
@@ -107,11 +107,25 @@ struct dsac_engine {
     uint32_t* d_k1_endw = nullptr;
     uint32_t* d_k1_accbits = nullptr;
     double* d_k1_pose = nullptr;
-    uint32_t* d_k1_wq = nullptr;
+    uint2* d_k1_wq = nullptr;
     uint32_t* d_k1_fq = nullptr;
     int* d_k1_counters = nullptr;                 // wq_n[K1S_MAX_ROUNDS], fq_n[K1S_MAX_ROUNDS]
     unsigned long long* d_k1_stats = nullptr;     // [2][2]: candidates / hypotheses of finished streams, by call parity
-    unsigned long long* d_k1_dbg = nullptr;       // [K1S_MAX_ROUNDS][4] (DSAC_K1_DEBUG=1), else null
+    unsigned long long* d_k1_dbg = nullptr;       // [K1S_MAX_ROUNDS][4] (DSAC_K1_DEBUG=1 or dsac_sampler_profile), else null
+    // dsac_sampler_profile: CUDA events between the sampler's launches of the last forward pass
+    int k1_profile = 0;
+    std::vector<cudaEvent_t> k1_ev;               // event i is recorded after launch i (event 0 before the first)
+    std::vector<int> k1_ev_kind;                  // 0 cells/slot (integer generation + selection), 1 filter, 2 solve, 3 resume tail
+    int k1_ev_n = 0;
+    // generator / filter overlap: k1_slot runs on the caller's stream, k1_filter + k1_solve on this side stream
+    cudaStream_t k1_side = nullptr;
+    cudaStream_t k1_side2 = nullptr;              // k1_solve, when it runs next to the following set's filter (overlap mode 2)
+    cudaEvent_t k1_ev_filt[K1S_MAX_SETS] = {};    // filter of launch set i done
+    cudaEvent_t k1_ev_solve[K1S_MAX_SETS] = {};   // solve of launch set i done
+    cudaEvent_t k1_ev_gen[K1S_MAX_SETS] = {};     // generation of launch set i done
+    cudaEvent_t k1_ev_round = nullptr;            // last solve of a round done
+    int k1_overlap = 1;
+    int k1_wq_stride = 0;
 };
 
 static int fail(dsac_engine* e, int code, const char* fmt, ...) {
@@ -192,6 +206,13 @@ void dsac_engine_destroy(dsac_engine* e) {
                 fprintf(stderr, "[dsac K1 split, last call] round %d: %llu active streams, %llu candidates, %llu flagged, %llu accepted\n", r,
                         h[r * 4], h[r * 4 + 1], h[r * 4 + 2], h[r * 4 + 3]);
     }
+    for (cudaEvent_t ev : e->k1_ev) cudaEventDestroy(ev);
+    if (e->k1_side) { cudaStreamSynchronize(e->k1_side); cudaStreamDestroy(e->k1_side); }
+    if (e->k1_side2) { cudaStreamSynchronize(e->k1_side2); cudaStreamDestroy(e->k1_side2); }
+    for (cudaEvent_t ev : e->k1_ev_filt) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->k1_ev_solve) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->k1_ev_gen) if (ev) cudaEventDestroy(ev);
+    if (e->k1_ev_round) cudaEventDestroy(e->k1_ev_round);
     void* k1ptrs[] = {e->d_k1_state, e->d_k1_celltab, e->d_k1_cells, e->d_k1_endw, e->d_k1_accbits, e->d_k1_pose, e->d_k1_wq,
                       e->d_k1_fq, e->d_k1_counters, e->d_k1_stats, e->d_k1_dbg};
     for (void* p : k1ptrs)
@@ -319,18 +340,35 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
     if (e->k1_mode) {
         const size_t T = (size_t)cfg->n_streams, slots = n * T;
         const int quota_max = (cfg->n_hyps + cfg->n_streams - 1) / cfg->n_streams;
-        int cap = std::min(K1S_MAX_CAP, std::max(256, 64 * quota_max));
-        cap = (cap + 255) & ~255;
+        int cap = std::min(K1S_MAX_CAP, std::max(1024, K1S_CAP_PER_HYP * quota_max));
+        cap = (cap + 1023) & ~1023;     // a round is generated in portions of cap / 4, themselves multiples of 256
         e->k1_cap = cap;
+        e->k1_wq_stride = (int)(slots * 128);
         CUC(cudaMalloc(&e->d_k1_state, slots * sizeof(K1SlotState)));
         CUC(cudaMalloc(&e->d_k1_celltab, n * N * sizeof(CellRec)));
         CUC(cudaMalloc(&e->d_k1_cells, slots * cap * sizeof(uint2)));
         CUC(cudaMalloc(&e->d_k1_endw, slots * cap * sizeof(uint32_t)));
         CUC(cudaMalloc(&e->d_k1_accbits, slots * (cap / 32) * sizeof(uint32_t)));
         CUC(cudaMalloc(&e->d_k1_pose, slots * cap * 6 * sizeof(double)));
-        CUC(cudaMalloc(&e->d_k1_wq, slots * 64 * sizeof(uint32_t)));
-        CUC(cudaMalloc(&e->d_k1_fq, slots * cap * sizeof(uint32_t)));
-        CUC(cudaMalloc(&e->d_k1_counters, 2 * K1S_MAX_ROUNDS * sizeof(int)));
+        CUC(cudaMalloc(&e->d_k1_wq, (size_t)K1S_MAX_SETS * slots * 128 * sizeof(uint2)));
+        CUC(cudaMalloc(&e->d_k1_fq, 2 * slots * cap * sizeof(uint32_t)));   // two regions: the filter of set k+1 writes one while the solve of set k reads the other
+        CUC(cudaMalloc(&e->d_k1_counters, 2 * K1S_MAX_SETS * sizeof(int)));
+        {   // the fp64 kernels get the higher priority: when a generator launch and a filter launch become ready together,
+            // the persistent filter CTAs are placed first and the generator's CTAs fill the registers they leave free
+            int least = 0, greatest = 0;
+            CUC(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            int prio = greatest;
+            if (const char* pr = getenv("DSAC_K1_SIDE_PRIO")) prio = atoi(pr) ? greatest : least;
+            CUC(cudaStreamCreateWithPriority(&e->k1_side, cudaStreamNonBlocking, prio));
+            CUC(cudaStreamCreateWithPriority(&e->k1_side2, cudaStreamNonBlocking, prio));
+            for (int i = 0; i < K1S_MAX_SETS; i++) {
+                CUC(cudaEventCreateWithFlags(&e->k1_ev_filt[i], cudaEventDisableTiming));
+                CUC(cudaEventCreateWithFlags(&e->k1_ev_solve[i], cudaEventDisableTiming));
+            }
+        }
+        for (int i = 0; i < K1S_MAX_SETS; i++) CUC(cudaEventCreateWithFlags(&e->k1_ev_gen[i], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&e->k1_ev_round, cudaEventDisableTiming));
+        if (const char* ov = getenv("DSAC_K1_OVERLAP")) e->k1_overlap = atoi(ov);
         CUC(cudaMalloc(&e->d_k1_stats, 4 * sizeof(unsigned long long)));
         CUC(cudaMemset(e->d_k1_stats, 0, 4 * sizeof(unsigned long long)));
         if (getenv("DSAC_K1_DEBUG")) CUC(cudaMalloc(&e->d_k1_dbg, K1S_MAX_ROUNDS * 4 * sizeof(unsigned long long)));
@@ -373,6 +411,36 @@ int dsac_set_tail_split(dsac_engine* e, int32_t mode) {
 }
 
 int64_t dsac_launch_count(const dsac_engine* e) { return e ? e->launches : 0; }
+
+int dsac_sampler_profile(dsac_engine* e, int32_t enable) {
+    if (!e) return DSAC_ERR_ARG;
+    if (!e->k1_mode) return fail(e, DSAC_ERR_ARG, "dsac_sampler_profile needs the split sampler (DSAC_K1_MODE unset)");
+    CU(cudaSetDevice(e->cfg.device));
+    if (enable && !e->d_k1_dbg) CU(cudaMalloc(&e->d_k1_dbg, K1S_MAX_ROUNDS * 4 * sizeof(unsigned long long)));
+    e->k1_profile = enable ? 1 : 0;
+    return DSAC_OK;
+}
+
+int dsac_sampler_profile_read(dsac_engine* e, double ms[4], uint64_t counts[4]) {
+    if (!e || !ms || !counts) return DSAC_ERR_ARG;
+    if (!e->k1_profile || e->k1_ev_n < 2) return fail(e, DSAC_ERR_ARG, "dsac_sampler_profile_read: no profiled forward pass");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventSynchronize(e->k1_ev[e->k1_ev_n - 1]));
+    for (int k = 0; k < 4; k++) { ms[k] = 0; counts[k] = 0; }
+    for (int i = 1; i < e->k1_ev_n; i++) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, e->k1_ev[i - 1], e->k1_ev[i]));
+        const int kind = e->k1_ev_kind[i];
+        if (kind >= 0 && kind < 4) ms[kind] += t;
+    }
+    unsigned long long h[K1S_MAX_ROUNDS * 4];
+    CU(cudaMemcpy(h, e->d_k1_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < K1S_MAX_ROUNDS; r++) {
+        counts[0] += h[r * 4 + 1]; counts[1] += h[r * 4 + 2]; counts[2] += h[r * 4 + 3];
+        if (h[r * 4 + 0]) counts[3] = (uint64_t)(r + 1);
+    }
+    return DSAC_OK;
+}
 
 int dsac_set_score_hook(dsac_engine* e, dsac_score_hook fn, void* user) {
     if (!e) return DSAC_ERR_ARG;
@@ -462,34 +530,90 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             q.cells = e->d_k1_cells + o * T * cap; q.endw = e->d_k1_endw + o * T * cap;
             q.accbits = e->d_k1_accbits + o * T * (cap / 32); q.pose_out = e->d_k1_pose + o * T * cap * 6;
             q.wq = e->d_k1_wq; q.fq = e->d_k1_fq;
-            q.wq_n = e->d_k1_counters; q.fq_n = e->d_k1_counters + K1S_MAX_ROUNDS;
+            q.wq_n = e->d_k1_counters; q.fq_n = e->d_k1_counters + K1S_MAX_SETS;
+            q.wq_stride = e->k1_wq_stride;
             const int par = (int)(e->k1_calls & 1ull);
             e->k1_calls++;
             q.stats_cur = e->d_k1_stats + 2 * par; q.stats_prev = e->d_k1_stats + 2 * (par ^ 1);
             q.dbg = e->d_k1_dbg;
             q.cap = e->k1_cap;
             const long long n_slots = (long long)n * c.n_streams;
-            q.chunk = std::min(e->k1_cap, n_slots >= 512 ? 2048 : (n_slots >= 64 ? 512 : 256));
-            if (const char* ch = getenv("DSAC_K1_CHUNK")) q.chunk = std::max(256, std::min(std::min(e->k1_cap, K1F_MAX_CHUNK), (atoi(ch) + 255) & ~255));
+            // a round is generated in up to 4 portions of cap / 4 candidates (round 0: 4, round 1: 2, later rounds: the whole
+            // round at once); a filter work item is a chunk of a portion
+            const int portion4 = e->k1_cap / 4;
+            int want_chunk = n_slots >= 512 ? 2048 : (n_slots >= 64 ? 512 : 256);
+            if (const char* ch = getenv("DSAC_K1_CHUNK")) want_chunk = std::max(256, atoi(ch));
+            q.chunk = 256;
+            for (int cc : {2048, 1024, 512, 256})
+                if (cc <= want_chunk && cc <= K1F_MAX_CHUNK && portion4 % cc == 0) { q.chunk = cc; break; }
             q.n_slots = (int)n_slots;
-            q.round = 0; q.select_only = 0;
-            CU(cudaMemsetAsync(e->d_k1_counters, 0, 2 * K1S_MAX_ROUNDS * sizeof(int), stream));
+            q.round = 0; q.select_only = 0; q.gen_only = 0;
+            CU(cudaMemsetAsync(e->d_k1_counters, 0, 2 * K1S_MAX_SETS * sizeof(int), stream));
             CU(cudaMemsetAsync(q.stats_cur, 0, 2 * sizeof(unsigned long long), stream));
             if (q.dbg) CU(cudaMemsetAsync(q.dbg, 0, K1S_MAX_ROUNDS * 4 * sizeof(unsigned long long), stream));
+            e->k1_ev_n = 0;
+            auto mark = [&](int kind) {   // dsac_sampler_profile: an event after every launch
+                if (!e->k1_profile) return;
+                if ((size_t)e->k1_ev_n >= e->k1_ev.size()) {
+                    cudaEvent_t ev;
+                    if (cudaEventCreate(&ev) != cudaSuccess) return;
+                    e->k1_ev.push_back(ev);
+                    e->k1_ev_kind.push_back(0);
+                }
+                e->k1_ev_kind[e->k1_ev_n] = kind;
+                cudaEventRecord(e->k1_ev[e->k1_ev_n++], stream);
+            };
+            // with the profile on everything runs on one stream so that the event intervals are the kernels' own durations
+            const bool overlap = e->k1_overlap && !e->k1_profile;
+            cudaStream_t side = overlap ? e->k1_side : stream;
+            cudaStream_t solve_side = (overlap && e->k1_overlap >= 2) ? e->k1_side2 : side;
+            const size_t n_slots_cap = (size_t)e->cfg.max_frames * c.n_streams * (size_t)e->k1_cap;
+            mark(-1);
             k1_cells<<<(unsigned)(((size_t)n * Nn + 255) / 256), 256, 0, stream>>>(q, n);
+            mark(0);
             e->launches++;
-            const int fgrid = (int)std::min<long long>(e->k1_filter_grid, n_slots * ((e->k1_cap + q.chunk - 1) / q.chunk));
+            int set = 0;
             for (int r = 0; r < e->k1_rounds; r++) {
+                // portions only pay when the generator has the whole GPU to fill (many streams); a few streams (single-frame
+                // latency, BASELINE config 2) take every round in one launch set: fewer dependent launches
+                const bool portioned = n_slots >= 128 && r < 2;
+                const int sets = portioned ? (r == 0 ? 4 : 2) : 1;
                 q.round = r;
-                k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
-                k1_filter<<<fgrid, K1F_THREADS, sizeof(K1FSmem), stream>>>(q);
-                k1_solve<<<e->k1_solve_grid, K1V_THREADS, 0, stream>>>(q);
-                e->launches += 3;
+                q.portion = portioned ? portion4 : e->k1_cap;
+                q.round_limit = q.portion * sets;
+                const int fgrid = (int)std::min<long long>(e->k1_filter_grid, n_slots * ((q.portion + q.chunk - 1) / q.chunk));
+                if (overlap && r > 0) CU(cudaStreamWaitEvent(stream, e->k1_ev_round, 0));   // the selection needs the previous round's solves
+                for (int k = 0; k < sets && set < K1S_MAX_SETS; k++, set++) {
+                    q.gen_only = (k > 0);
+                    q.qidx = set;
+                    q.fq = e->d_k1_fq + (size_t)(set & 1) * (size_t)n_slots_cap;
+                    k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
+                    mark(0);
+                    if (overlap) {
+                        CU(cudaEventRecord(e->k1_ev_gen[set], stream));
+                        CU(cudaStreamWaitEvent(side, e->k1_ev_gen[set], 0));
+                        if (solve_side != side && set >= 2) CU(cudaStreamWaitEvent(side, e->k1_ev_solve[set - 2], 0));   // the flag-queue region is free again
+                    }
+                    k1_filter<<<fgrid, K1F_THREADS, sizeof(K1FSmem), side>>>(q);
+                    if (!overlap) mark(1);
+                    if (solve_side != side) {
+                        CU(cudaEventRecord(e->k1_ev_filt[set], side));
+                        CU(cudaStreamWaitEvent(solve_side, e->k1_ev_filt[set], 0));
+                    }
+                    k1_solve<<<e->k1_solve_grid, K1V_THREADS, 0, solve_side>>>(q);
+                    if (solve_side != side) CU(cudaEventRecord(e->k1_ev_solve[set], solve_side));
+                    if (!overlap) mark(2);
+                    e->launches += 3;
+                }
+                if (overlap) CU(cudaEventRecord(e->k1_ev_round, solve_side));
             }
-            q.round = e->k1_rounds; q.select_only = 1;
+            if (overlap) CU(cudaStreamWaitEvent(stream, e->k1_ev_round, 0));
+            q.round = e->k1_rounds; q.select_only = 1; q.gen_only = 0;
             k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
+            mark(0);
             sp.resume = q.state;   // streams the rounds left unfinished (normally none) continue in the monolithic kernel
             k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);
+            mark(3);
             e->launches += 2;
             CU(cudaGetLastError());
         }

@@ -41,6 +41,34 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total, int* s_warp /*
     return base + incl - v;
 }
 
+// ------------------------------------------------------------------ TMA staging helpers
+// 1-D bulk copy global -> shared memory (cp.async.bulk, SASS UBLKCP) completing on a transaction barrier: one thread
+// issues it, everybody who reads the data waits on the barrier.  Sizes and addresses are multiples of 16 bytes.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* mbar) {
+    const uint32_t d = smem_addr_u32(dst_smem), m = smem_addr_u32(mbar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy reads of the buffer are done (barrier), order them before the async write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src_gmem), "r"(bytes), "r"(m)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, uint32_t parity) {
+    const uint32_t m = smem_addr_u32(mbar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DSAC_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra DSAC_MBAR_WAIT_%=;\n"
+        "}\n" ::"r"(m), "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long* mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ K1: sampling
 constexpr int K1S_LEFT_CAP = 2048;               // decoded words carried from one round of the split sampler to the next
 
@@ -55,6 +83,8 @@ struct K1SlotState {
     int32_t left_n;             // decoded words [pos, gen) kept in left[]
     int32_t any_reject;         // left[] contains a rejected draw (value 255)
     int32_t overflow;           // leftover did not fit (cannot happen with the window sizes used; checked by the host)
+    int32_t target;             // candidates the current round shall reach (generated in portions, see sampler_split.cuh)
+    int32_t pad_;
     long long cand_base;        // candidates consumed before the current round
     unsigned char left[K1S_LEFT_CAP];
 };
@@ -806,7 +836,8 @@ __device__ __noinline__ void score_tile_guarded(const float* s_P, int nh, const 
 #endif
 template <bool WRITE_DM>
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_BLOCKS) k_score(ScoreParams p) {
-    __shared__ __align__(16) float s_P[K2_MAX_TILE * 12];
+    __shared__ __align__(128) float s_P[K2_MAX_TILE * 12];
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ float s_part[K2_WARPS][K2_MAX_TILE];
     __shared__ double s_red[8 * K2_WARPS];
     __shared__ unsigned int s_last;
@@ -833,13 +864,12 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_BLOCKS) k_score(ScoreParams
                 pv[j] = (float)q.y - p.cyf;
             }
         }
-        // stage the tile's 3x4 projection rows in shared memory
-        {
-            const float4* src = reinterpret_cast<const float4*>(p.hyp_P + ((size_t)frame * p.H + hbeg) * 12);
-            float4* dst = reinterpret_cast<float4*>(s_P);
-            for (int i = tid; i < nh * 3; i += K2_THREADS) dst[i] = __ldg(src + i);
-        }
+        // stage the tile's 3x4 projection rows (48 bytes per hypothesis, contiguous) in shared memory by TMA: one thread
+        // issues the bulk copy while the others are still converting their scene coordinates; everybody waits on the barrier
+        if (tid == 0) mbar_init(&s_bar);
         __syncthreads();
+        if (tid == 0) tma_load_1d(s_P, p.hyp_P + ((size_t)frame * p.H + hbeg) * 12, (uint32_t)nh * 48u, &s_bar);
+        mbar_wait(&s_bar, 0u);
 
         float* dm = WRITE_DM ? p.diffmaps + ((size_t)frame * p.H + hbeg) * DSAC_N_CONST : nullptr;
         const float tau_k = p.thr * p.kbeta;

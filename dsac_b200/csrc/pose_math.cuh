@@ -738,9 +738,16 @@ DSAC_HDN bool minimal_set_hypothesis(const float obj[12], const float img[8], do
 // DSAC_FLAG(k): "needs the full solve", k = which guard fired (counted only in the host statistics build)
 #if defined(DSAC_FILTER_STATS) && !defined(__CUDA_ARCH__)
 static long long g_filter_reason[24];
+static double g_filter_fp32_maxdev = 0;
 #define DSAC_FLAG(k) (g_filter_reason[k]++, true)
 #else
 #define DSAC_FLAG(k) true
+#endif
+#ifndef DSAC_FILTER_FP32_TAIL
+#define DSAC_FILTER_FP32_TAIL 1        /* 4th-point stage of the conservative filter in fp32 with a widened band (else fp64) */
+#endif
+#ifndef DSAC_FILTER_FP32_BAND
+#define DSAC_FILTER_FP32_BAND 0.25     /* px: candidates whose 4th point lands within thr + 0.25 px go to the full solve (fp32 deviates <= 0.007 px) */
 #endif
 #ifndef DSAC_FILTER_UNROLL
 #define DSAC_FILTER_UNROLL 1   /* root slots evaluated per trip of the filter's root loop (register pressure vs ILP) */
@@ -785,6 +792,9 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         nroots = quartic_roots_banded(c4, c3, c2, c1, c0, xr, &uncertain);
         flag |= uncertain;                                                               // (4)
     }
+#if defined(DSAC_FILTER_STATS) && !defined(__CUDA_ARCH__)
+    g_filter_reason[20 + nroots / 2]++;   // statistics build: candidates with 0 / 2 / 4 real roots (the roofline's flop model)
+#endif
     // world triangle frame and the 4th point's coordinates in it
     const double inv_d = filt_rsqrt(s01), inv_n = filt_rsqrt(nn), d01 = s01 * inv_d;
     const double e1x = ax * inv_d, e1y = ay * inv_d, e1z = az * inv_d;
@@ -793,9 +803,18 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
     const double wx = X[3][0] - X[0][0], wy = X[3][1] - X[0][1], wz = X[3][2] - X[0][2];
     const double al = wx * e1x + wy * e1y + wz * e1z, be = wx * e2x + wy * e2y + wz * e2z, ga = wx * e3x + wy * e3y + wz * e3z;
     const double lim2 = (thr + DSAC_FILTER_BAND_PX) * (thr + DSAC_FILTER_BAND_PX);
-    constexpr int kRootUnroll = DSAC_FILTER_UNROLL;
-#pragma unroll kRootUnroll
-    for (int i = 0; i < 4; i++) {
+#if DSAC_FILTER_FP32_TAIL
+    const float b0x = (float)bear[0][0], b0y = (float)bear[0][1], b0z = (float)bear[0][2];
+    const float b1x = (float)bear[1][0], b1y = (float)bear[1][1], b1z = (float)bear[1][2];
+    const float b2x = (float)bear[2][0], b2y = (float)bear[2][1], b2z = (float)bear[2][2];
+    const float d01f = (float)d01, inv_df = (float)inv_d, inv_nf = (float)inv_n;
+    const float alf = (float)al, bef = (float)be, gaf = (float)ga, ff = (float)f, du3f = (float)(mu3 - cx), dv3f = (float)(mv3 - cy);
+    const float lim2f = (float)((thr + DSAC_FILTER_FP32_BAND) * (thr + DSAC_FILTER_FP32_BAND));
+    const bool illcond = !(nn > 1e-3 * s01 * s02);   // sin^2 of the world triangle's angle at point 0: cross products lose 1 / sin of their digits
+#endif
+    // 96.9 % of the candidates have exactly two real roots, 0.7 % four (tools/filter_stats.py): slots 0 and 1 are evaluated
+    // by every lane, slots 2 and 3 only by the lanes that have them (a divergent branch one warp in five takes).
+    auto root_slot = [&](int i) {
         double x = (i == 0) ? xr[0] : (i == 1) ? xr[1] : (i == 2) ? xr[2] : xr[3];
         const double Dn = D1 * x + D0;
         const bool f5 = !(fabs(Dn) > 1.1e-3 * (fabs(D1 * x) + fabs(D0)));   // (the full solve switches formula at 1e-3)
@@ -816,6 +835,49 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         const bool f8 = (x < 1e-6) | (y < 1e-6);           // borderline positivity
         const double v = x * x + y * y - x * y * r;
         const bool f9 = !(v > 1e-12);
+#if DSAC_FILTER_FP32_TAIL
+        // The 4th point's camera position and pixel error in fp32 (FMA pipe, idle in this kernel) instead of fp64: (x, y) are
+        // polished in fp64 above; from here on the quantities are lengths of ~10^2..10^4 mm combined without dangerous
+        // cancellation unless the triangle is nearly degenerate (guarded: cond below).  Measured on 2 * 10^6 benchmark
+        // candidates (tools/filter_stats.py, statistics build): |pixel error fp32 - fp64| <= DSAC_FILTER_FP32_MAXDEV px; the
+        // threshold band is widened from 0.05 px to DSAC_FILTER_FP32_BAND px to cover it many times over.
+        const float xf = (float)x, yf = (float)y;
+        const float Zf = d01f * DSAC_RSQRTF_EARLY((float)v);
+        const float L0 = xf * Zf, L1 = yf * Zf;
+        const float M0x = L0 * b0x, M0y = L0 * b0y, M0z = L0 * b0z;
+        const float ux = L1 * b1x - M0x, uy = L1 * b1y - M0y, uz = L1 * b1z - M0z;
+        const float vx = Zf * b2x - M0x, vy = Zf * b2y - M0y, vz = Zf * b2z - M0z;
+        const float cxn = uy * vz - uz * vy, cyn = uz * vx - ux * vz, czn = ux * vy - uy * vx;
+        const float c1x = ux * inv_df, c1y = uy * inv_df, c1z = uz * inv_df;
+        const float c3x = cxn * inv_nf, c3y = cyn * inv_nf, c3z = czn * inv_nf;
+        const float c2x = c3y * c1z - c3z * c1y, c2y = c3z * c1x - c3x * c1z, c2z = c3x * c1y - c3y * c1x;
+        const float X3 = M0x + alf * c1x + bef * c2x + gaf * c3x;
+        const float Y3 = M0y + alf * c1y + bef * c2y + gaf * c3y;
+        const float Z3 = M0z + alf * c1z + bef * c2z + gaf * c3z;
+        const float gu = ff * X3 - du3f * Z3, gv = ff * Y3 - dv3f * Z3, zz = Z3 * Z3;
+        // depth of the 4th point not tiny against the lengths it was summed from: the fp32 error of Z3 is ~10 eps (sum), so above
+        // this guard Z3 is good to 0.6 %, i.e. 0.06 px on an error at the 10 px threshold (a larger error need not be accurate)
+        const bool shallow = !(fabsf(Z3) > 2e-4f * (fabsf(M0z) + fabsf(alf) + fabsf(bef) + fabsf(gaf)));
+        const bool f10 = (!(gu * gu + gv * gv > lim2f * zz)) | (!(zz > 0.f)) | shallow | illcond;
+#if defined(DSAC_FILTER_STATS) && !defined(__CUDA_ARCH__)
+        {   // statistics build: the same quantity in fp64, to record the largest deviation of the fp32 pixel error
+            const double Zd = d01 * filt_rsqrt(v), l0 = x * Zd, l1 = y * Zd;
+            const double m0x = l0 * bear[0][0], m0y = l0 * bear[0][1], m0z = l0 * bear[0][2];
+            const double Ux = l1 * bear[1][0] - m0x, Uy = l1 * bear[1][1] - m0y, Uz = l1 * bear[1][2] - m0z;
+            const double Vx = Zd * bear[2][0] - m0x, Vy = Zd * bear[2][1] - m0y, Vz = Zd * bear[2][2] - m0z;
+            const double Cx = Uy * Vz - Uz * Vy, Cy = Uz * Vx - Ux * Vz, Cz = Ux * Vy - Uy * Vx;
+            const double k1x = Ux * inv_d, k1y = Uy * inv_d, k1z = Uz * inv_d, k3x = Cx * inv_n, k3y = Cy * inv_n, k3z = Cz * inv_n;
+            const double k2x = k3y * k1z - k3z * k1y, k2y = k3z * k1x - k3x * k1z, k2z = k3x * k1y - k3y * k1x;
+            const double X3d = m0x + al * k1x + be * k2x + ga * k3x, Y3d = m0y + al * k1y + be * k2y + ga * k3y, Z3d = m0z + al * k1z + be * k2z + ga * k3z;
+            const double e64 = sqrt((f * X3d / Z3d - (mu3 - cx)) * (f * X3d / Z3d - (mu3 - cx)) + (f * Y3d / Z3d - (mv3 - cy)) * (f * Y3d / Z3d - (mv3 - cy)));
+            const double e32 = sqrt((double)(gu * gu + gv * gv)) / fabs((double)Z3);
+            if (i < nroots && !neg && !(f5 | f6 | f7 | f8 | f9) && !shallow && !illcond && e64 < 200.0) {
+                const double dev = fabs(e32 - e64);
+                if (dev > g_filter_fp32_maxdev) g_filter_fp32_maxdev = dev;
+            }
+        }
+#endif
+#else
         const double Z = d01 * filt_rsqrt(v);
         const double L0 = x * Z, L1 = y * Z;
         const double M0x = L0 * bear[0][0], M0y = L0 * bear[0][1], M0z = L0 * bear[0][2];
@@ -831,11 +893,18 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
         // |(cx + f X3 / Z3 - mu3, cy + f Y3 / Z3 - mv3)|^2 > lim2, multiplied through by Z3^2 (no division)
         const double gu = f * X3 - (mu3 - cx) * Z3, gv = f * Y3 - (mv3 - cy) * Z3, zz = Z3 * Z3;
         const bool f10 = (!(gu * gu + gv * gv > lim2 * zz)) | (!(zz > 0));
+#endif
         const bool root_flag = f5 | f6 | f7 | ((!neg) & (f8 | f9 | f10));
 #if defined(DSAC_FILTER_STATS) && !defined(__CUDA_ARCH__)
         if (!flag && i < nroots && root_flag) g_filter_reason[f5 ? 5 : f6 ? 6 : f7 ? 7 : f8 ? 8 : f9 ? 9 : 10]++;
 #endif
         flag |= (i < nroots) & root_flag;
+    };
+    root_slot(0);
+    root_slot(1);
+    if (nroots > 2) {
+        root_slot(2);
+        root_slot(3);
     }
     return flag;
 }

@@ -30,8 +30,8 @@ DSAC_HD uint32_t mt_temper(uint32_t y) {
 }
 
 DSAC_HD uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
-    uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
-    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+    return far ^ (y >> 1) ^ ((0u - (nxt & 1u)) & 0x9908b0dfu);
 }
 
 DSAC_HD void mt_seed(uint32_t* mt, uint32_t seed) {

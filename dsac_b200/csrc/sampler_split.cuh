@@ -26,16 +26,29 @@
 
 namespace dsac {
 
-constexpr int K1S_THREADS = 256;                 // k1_slot
+#define K1S_THREADS_DEF 256
+constexpr int K1S_THREADS = K1S_THREADS_DEF;     // k1_slot
 constexpr int K1S_WARPS = K1S_THREADS / 32;
 constexpr int K1S_SR = 2048;                     // candidates per generator window (super-round)
 constexpr int K1S_WORDS = K1S_SR * 8 + 1024;     // decoded stream words buffered per window
-constexpr int K1S_MAX_CAP = 16384;               // candidates per stream and round (flag queue entries hold 14 bits)
+constexpr int K1S_MAX_CAP = 32768;               // candidates per stream and round (flag queue entries hold 15 bits)
+constexpr int K1S_IDX_BITS = 15;
+constexpr int K1S_SEL_WORDS = K1S_MAX_CAP / 32 / K1S_THREADS_DEF;   // accept-bit words per thread in the selection
 constexpr int K1S_ACC_LIST = 1024;               // accepted candidates selected per stream and round (<= quota <= DSAC_MAX_HYPS)
 constexpr int K1F_THREADS = 256;                 // k1_filter
 constexpr int K1F_MAX_CHUNK = 2048;              // candidates per filter work item (multiple of K1F_THREADS)
 constexpr int K1V_THREADS = 128;                 // k1_solve: 32 groups of 4 lanes
 constexpr int K1S_MAX_ROUNDS = 16;
+#ifndef K1S_CAP_PER_HYP
+#define K1S_CAP_PER_HYP 64       /* round capacity in candidates per hypothesis of the stream (cap = 16 384 at 256 hypotheses; 96 measured the same) */
+#endif
+#ifndef K1S_FIRST_ROUND_FRAC
+#define K1S_FIRST_ROUND_FRAC 0.9   /* first round: this fraction of what the previous call's streams needed */
+#endif
+#ifndef K1S_MARGIN_SIGMA
+#define K1S_MARGIN_SIGMA 2.0       /* later rounds: margin in standard deviations of the binomial accept count */
+#endif
+constexpr int K1S_MAX_SETS = 32;                  // launch sets (portions) per call
 
 struct K1SplitParams {
     SampleParams sp;            // inputs / outputs of k_sample
@@ -45,10 +58,10 @@ struct K1SplitParams {
     uint32_t* endw;             // [slots][cap]   stream position after the candidate
     uint32_t* accbits;          // [slots][cap/32]
     double* pose_out;           // [slots][cap][6] rvec, tvec of accepted candidates
-    uint32_t* wq;               // filter work items: slot * 64 + chunk
-    uint32_t* fq;               // flagged candidates: slot << 14 | index
-    int* wq_n;                  // [K1S_MAX_ROUNDS]
-    int* fq_n;                  // [K1S_MAX_ROUNDS]
+    uint2* wq;                  // filter work items of launch set `qidx`: (slot * 128 + chunk, candidates in the chunk)
+    uint32_t* fq;               // flagged candidates: slot << K1S_IDX_BITS | index
+    int* wq_n;                  // [K1S_MAX_SETS] per launch set
+    int* fq_n;                  // [K1S_MAX_SETS]
     unsigned long long* stats_cur;   // [2] candidates, accepted hypotheses of the streams finished in this call
     const unsigned long long* stats_prev;   // the same of the previous call (prior for the first round's size)
     unsigned long long* dbg;    // [K1S_MAX_ROUNDS][4] or null: active streams, candidates, flagged, accepted per round
@@ -57,6 +70,15 @@ struct K1SplitParams {
     int n_slots;
     int round;                  // >= 0; select_only: no generation
     int select_only;
+    // A round is generated in portions (launch sets): the first k1_slot of a round selects, sizes the round and generates
+    // up to `portion` candidates; the following ones (gen_only) append the next `portion` of the same round.  Every
+    // launch set has its own work / flag queue (index qidx), so the generator of set k+1 can run on a second stream
+    // while filter and solve work on set k (integer pipe next to the fp64 pipe).
+    int gen_only;
+    int portion;                // candidates per launch set (multiple of chunk)
+    int round_limit;            // candidates a round may have at most (= portion * launch sets of the round)
+    int qidx;                   // launch set of this call: index into wq_n / fq_n, wq region qidx * wq_stride
+    int wq_stride;
 };
 
 // ------------------------------------------------------------------ k1_cells
@@ -101,13 +123,13 @@ struct K1GSmem {
 __device__ __forceinline__ int k1_round_size(int quota, int acc, long long cand_base, int cap, long long cand_left, double prior_cpa) {
     double n;
     if (cand_base == 0) {
-        n = (prior_cpa > 0) ? 0.8 * prior_cpa * quota : 16.0 * quota;
+        n = (prior_cpa > 0) ? K1S_FIRST_ROUND_FRAC * prior_cpa * quota : 16.0 * quota;
         if (n < 64) n = 64;
     } else if (acc == 0) {
         n = 4.0 * (double)cand_base;
     } else {
         const double need = (double)(quota - acc), cpa = (double)cand_base / (double)acc;
-        n = (need + 2.5 * sqrt(need) + 1.0) * cpa;
+        n = (need + K1S_MARGIN_SIGMA * sqrt(need) + 1.0) * cpa;
     }
     if (n > (double)cap) n = (double)cap;
     if (n > (double)cand_left) n = (double)cand_left;
@@ -116,7 +138,10 @@ __device__ __forceinline__ int k1_round_size(int quota, int acc, long long cand_
     return r;
 }
 
-__global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
+#ifndef K1S_MIN_BLOCKS
+#define K1S_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitParams q) {
     __shared__ K1GSmem sm;
     const SampleParams& p = q.sp;
     const int tid = threadIdx.x, lane = tid & 31, warp_id = tid >> 5;
@@ -131,10 +156,28 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
     uint32_t pos, gen;
     int acc;
     long long cand_base;
-    if (q.round == 0) {
+    int already = 0;          // candidates of this round generated by earlier launch sets
+    if (q.gen_only) {
+        // ---------------- a further portion of the current round: restore the generator, nothing to select
+        if (quota == 0 || S.done) return;
+        already = S.n_round;
+        if (already >= S.target) return;
+        acc = S.acc;
+        cand_base = S.cand_base;
+        pos = S.pos;
+        gen = S.gen;
+        {
+            uint32_t* half = sm.st + ((gen / MT_N) & 1u) * MT_N;
+            for (int k = tid; k < MT_N; k += K1S_THREADS) half[k] = S.mt[k];
+            const int ln = S.left_n;
+            for (int k = tid; k < ln; k += K1S_THREADS) sm.vals[k] = S.left[k];
+            if (tid == 0) { sm.any_reject = S.any_reject; sm.walk_fail = 0; }
+        }
+        __syncthreads();
+    } else if (q.round == 0) {
         if (quota == 0) {
             if (tid == 0) {
-                S.done = 1; S.acc = 0; S.n_round = 0; S.cand_base = 0; S.left_n = 0; S.any_reject = 0; S.overflow = 0; S.pos = 0; S.gen = 0;
+                S.done = 1; S.acc = 0; S.n_round = 0; S.target = 0; S.cand_base = 0; S.left_n = 0; S.any_reject = 0; S.overflow = 0; S.pos = 0; S.gen = 0;
                 p.stream_ncand[slot] = 0;
                 p.stream_endpos[slot] = 0;
             }
@@ -154,27 +197,28 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
         acc = S.acc;
         cand_base = S.cand_base;
         const int n_prev = S.n_round;
-        const int n_words = (n_prev + 31) >> 5;          // <= 512
+        const int n_words = (n_prev + 31) >> 5;          // <= K1S_MAX_CAP / 32
         const uint32_t* ab = q.accbits + (size_t)slot * (q.cap >> 5);
-        uint32_t w0 = 0, w1 = 0;
-        if (2 * tid < n_words) w0 = ab[2 * tid];
-        if (2 * tid + 1 < n_words) w1 = ab[2 * tid + 1];
-        const int c0 = __popc(w0), c1 = __popc(w1);
+        uint32_t w[K1S_SEL_WORDS];
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < K1S_SEL_WORDS; k++) {
+            const int wi = K1S_SEL_WORDS * tid + k;
+            w[k] = (wi < n_words) ? ab[wi] : 0u;
+            mine += __popc(w[k]);
+        }
         int tot;
-        int rank = block_excl_scan<K1S_WARPS>(c0 + c1, &tot, sm.warp[0]);
+        int rank = block_excl_scan<K1S_WARPS>(mine, &tot, sm.warp[0]);
         const int room = quota - acc;
-        {
-            uint32_t w = w0;
-            int base_i = 2 * tid * 32;
-            for (int half = 0; half < 2; half++) {
-                while (w) {
-                    const int b = __ffs(w) - 1;
-                    w &= w - 1;
-                    if (rank < room) sm.acc_list[rank] = (unsigned short)(base_i + b);
-                    rank++;
-                }
-                w = w1;
-                base_i += 32;
+#pragma unroll
+        for (int k = 0; k < K1S_SEL_WORDS; k++) {
+            uint32_t ww = w[k];
+            const int base_i = (K1S_SEL_WORDS * tid + k) * 32;
+            while (ww) {
+                const int b = __ffs(ww) - 1;
+                ww &= ww - 1;
+                if (rank < room) sm.acc_list[rank] = (unsigned short)(base_i + b);
+                rank++;
             }
         }
         __syncthreads();
@@ -205,7 +249,7 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
         if (q.dbg && tid == 0) atomicAdd(q.dbg + (size_t)(q.round - 1) * 4 + 3, (unsigned long long)tot);
         if (acc + n_emit >= quota) {
             if (tid == 0) {
-                S.done = 1; S.acc = quota; S.cand_base = cand_base + n_prev; S.n_round = 0;
+                S.done = 1; S.acc = quota; S.cand_base = cand_base + n_prev; S.n_round = 0; S.target = 0;
                 atomicAdd(q.stats_cur + 0, (unsigned long long)(cand_base + sm.acc_list[room - 1] + 1));
                 atomicAdd(q.stats_cur + 1, (unsigned long long)quota);
             }
@@ -214,7 +258,7 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
         acc += n_emit;
         cand_base += n_prev;
         if (q.select_only || cand_base >= cand_max) {   // the resume pass of k_sample takes over from here
-            if (tid == 0) { S.acc = acc; S.cand_base = cand_base; S.n_round = 0; }
+            if (tid == 0) { S.acc = acc; S.cand_base = cand_base; S.n_round = 0; S.target = 0; }
             return;
         }
         // ---------------- restore the generator
@@ -230,10 +274,16 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
         __syncthreads();
     }
 
-    // ---------------- size of this round
-    double prior = 0;
-    if (q.stats_prev && q.stats_prev[1] > 0) prior = (double)q.stats_prev[0] / (double)q.stats_prev[1];
-    const int n_round = k1_round_size(quota, acc, cand_base, q.cap, cand_max - cand_base, prior);
+    // ---------------- size of this round (first launch set of the round), size of this portion
+    int round_total;
+    if (q.gen_only) {
+        round_total = S.target;
+    } else {
+        double prior = 0;
+        if (q.stats_prev && q.stats_prev[1] > 0) prior = (double)q.stats_prev[0] / (double)q.stats_prev[1];
+        round_total = k1_round_size(quota, acc, cand_base, min(q.cap, q.round_limit), cand_max - cand_base, prior);
+    }
+    const int n_round = min(q.portion, round_total - already);   // candidates this launch generates
 
     // ---------------- generation: windows of up to K1S_SR candidates (phases A1, A2 and E of k_sample)
     int produced = 0;
@@ -246,23 +296,30 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
             const uint32_t* so = sm.st + st_par * MT_N;           // old state
             uint32_t* sn = sm.st + (st_par ^ 1u) * MT_N;            // new state
             st_par ^= 1u;
+            const int base_off = (int)(gen - pos);
+            const bool all_in = base_off >= 0 && base_off + MT_N <= K1S_WORDS;   // the usual case: no per-word window test
             if (tid < K1_WAVE) {
                 uint32_t x[3];
                 const bool has3 = mt_regenerate_words(so, tid, x) == 3;
+                bool rej_any = false;
 #pragma unroll
                 for (int w = 0; w < 3; w++) {
                     if (w < 2 || has3) {
                         const int k = tid + w * K1_WAVE;
                         sn[k] = x[w];
-                        const int off = (int)(gen - pos) + k;
-                        if (off >= 0 && off < K1S_WORDS) {
-                            const uint64_t prod = (uint64_t)mt_temper(x[w]) * DSAC_GRID_CONST;
-                            const bool rej = (uint32_t)prod < ((0u - DSAC_GRID_CONST) % DSAC_GRID_CONST);  // Lemire: low < 2^32 mod 40
-                            sm.vals[off] = rej ? (unsigned char)255 : (unsigned char)(prod >> 32);
-                            if (rej) sm.any_reject = 1;
+                        // libstdc++'s Lemire down-scaling of a 32-bit word to [0, 40): value = high half of w * 40,
+                        // re-drawn if the low half is < 2^32 mod 40 = 16
+                        const uint32_t tv = mt_temper(x[w]);
+                        const uint32_t hi = __umulhi(tv, (uint32_t)DSAC_GRID_CONST), lo = tv * (uint32_t)DSAC_GRID_CONST;
+                        const bool rej = lo < ((0u - DSAC_GRID_CONST) % DSAC_GRID_CONST);
+                        const int off = base_off + k;
+                        if (all_in || (off >= 0 && off < K1S_WORDS)) {
+                            sm.vals[off] = rej ? (unsigned char)255 : (unsigned char)hi;
+                            rej_any |= rej;
                         }
                     }
                 }
+                if (rej_any) sm.any_reject = 1;
             }
             gen += MT_N;
             __syncthreads();
@@ -419,8 +476,8 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
         for (int i = tid; i < n_sr; i += K1S_THREADS) {
             int cells[4];
             cand_parse_fast(sm.vals, sm.cand_start[i], w_avail, cells);
-            q.cells[cbase + produced + i] = make_uint2((uint32_t)cells[0] | ((uint32_t)cells[1] << 16), (uint32_t)cells[2] | ((uint32_t)cells[3] << 16));
-            q.endw[cbase + produced + i] = pos + (uint32_t)sm.cand_start[i + 1];
+            q.cells[cbase + already + produced + i] = make_uint2((uint32_t)cells[0] | ((uint32_t)cells[1] << 16), (uint32_t)cells[2] | ((uint32_t)cells[3] << 16));
+            q.endw[cbase + already + produced + i] = pos + (uint32_t)sm.cand_start[i + 1];
         }
 
         // advance the stream: the unread tail of the window moves to the front
@@ -455,25 +512,29 @@ __global__ void __launch_bounds__(K1S_THREADS) k1_slot(K1SplitParams q) {
         if (n_sr == 0) break;   // (cannot happen: every window holds at least one candidate)
     }
 
-    // ---------------- hand the round over: state, work items, cleared accept bits
+    // ---------------- hand the portion over: state, work items, cleared accept bits
     {
         const int left = min((int)(gen - pos), K1S_LEFT_CAP);
         const uint32_t* half = sm.st + ((gen / MT_N) & 1u) * MT_N;
         for (int k = tid; k < MT_N; k += K1S_THREADS) S.mt[k] = half[k];
         for (int k = tid; k < left; k += K1S_THREADS) S.left[k] = sm.vals[k];
-        uint32_t* ab = q.accbits + (size_t)slot * (q.cap >> 5);
+        uint32_t* ab = q.accbits + (size_t)slot * (q.cap >> 5) + (already >> 5);   // `already` is a multiple of the chunk size
         for (int k = tid; k < ((produced + 31) >> 5); k += K1S_THREADS) ab[k] = 0u;
         if (tid == 0) {
-            S.pos = pos; S.gen = gen; S.acc = acc; S.cand_base = cand_base; S.n_round = produced; S.done = 0;
+            S.pos = pos; S.gen = gen; S.acc = acc; S.cand_base = cand_base; S.n_round = already + produced; S.done = 0;
+            if (!q.gen_only) S.target = round_total;
             S.left_n = left; S.any_reject = sm.any_reject;
-            if (q.round == 0) S.overflow = 0;
+            if (q.round == 0 && !q.gen_only) S.overflow = 0;
             const int n_items = (produced + q.chunk - 1) / q.chunk;
             if (n_items > 0) {
-                const int at = atomicAdd(q.wq_n + q.round, n_items);
-                for (int c = 0; c < n_items; c++) q.wq[at + c] = (uint32_t)slot * 64u + (uint32_t)c;
+                const int at = atomicAdd(q.wq_n + q.qidx, n_items);
+                uint2* wq = q.wq + (size_t)q.qidx * q.wq_stride;
+                const int c0 = already / q.chunk;
+                for (int c = 0; c < n_items; c++)
+                    wq[at + c] = make_uint2((uint32_t)slot * 128u + (uint32_t)(c0 + c), (uint32_t)min(q.chunk, produced - c * q.chunk));
             }
             if (q.dbg) {
-                atomicAdd(q.dbg + (size_t)q.round * 4 + 0, 1ull);
+                if (!q.gen_only) atomicAdd(q.dbg + (size_t)q.round * 4 + 0, 1ull);
                 atomicAdd(q.dbg + (size_t)q.round * 4 + 1, (unsigned long long)produced);
             }
         }
@@ -500,43 +561,74 @@ __device__ __forceinline__ bool k1_filter_candidate(const CellRec* cell, const i
     return p3p_quick_core(bear, X, mu3, mv3, f, cx, cy, thr);
 }
 
-#ifndef K1F_MIN_BLOCKS
-#define K1F_MIN_BLOCKS 2
+#ifndef K1F_MAXREG
+#define K1F_MAXREG 128   /* measured: 128 registers (no spills) beat 96 (+8 % filter time) even though 96 would leave room for a co-resident generator CTA */
 #endif
 struct K1FSmem {
-    CellRec cell[DSAC_N_CONST];
+    CellRec cell[2][DSAC_N_CONST];            // the frame's cell table, double-buffered: 2 x 38.4 KB
     unsigned short wlist[K1F_THREADS / 32][K1F_MAX_CHUNK / (K1F_THREADS / 32)];   // per warp: flagged candidates of its share of the item
+    unsigned long long mbar[2];               // one transaction barrier per buffer
 };
 
-// One work item = up to `chunk` consecutive candidates of one stream.  The CTA stages the frame's cell table (only when
-// the frame changes); after that its warps run independently: a warp filters every 8th group of 32 candidates of the
-// item (coalesced 8-byte loads of the cell indices, the next group's prefetched), keeps the flagged ones in its own
-// list and appends them to the global queue with one atomic per item.  No block barrier except around the staging.
-__global__ void __launch_bounds__(K1F_THREADS, K1F_MIN_BLOCKS) k1_filter(K1SplitParams q) {
-    extern __shared__ __align__(16) unsigned char k1f_smem_raw[];
+// The frame's 38 400-byte cell table reaches shared memory by TMA (tma_load_1d, kernels.cuh): one thread issues the bulk
+// copy, the CTA waits on the transaction barrier, and the table of the NEXT work item is fetched into the other buffer
+// while the warps filter the current one.
+// One work item = up to `chunk` consecutive candidates of one stream.  After the cell table is in shared memory the
+// warps run independently: a warp filters every 8th group of 32 candidates of the item (coalesced 8-byte loads of the
+// cell indices, the next group's prefetched), keeps the flagged ones in its own list and appends them to the global
+// queue with one atomic per item.  A block barrier only when the CTA moves on to another frame's table.
+__global__ void __maxnreg__(K1F_MAXREG) k1_filter(K1SplitParams q) {
+    extern __shared__ __align__(128) unsigned char k1f_smem_raw[];
     K1FSmem& sm = *reinterpret_cast<K1FSmem*>(k1f_smem_raw);
     const SampleParams& p = q.sp;
     const int tid = threadIdx.x, lane = tid & 31, warp_id = tid >> 5;
-    const int n_items = q.wq_n[q.round];
+    const int n_items = q.wq_n[q.qidx];
+    const uint2* wq = q.wq + (size_t)q.qidx * q.wq_stride;
     const double inv_f = 1. / p.f, cx_f = p.cx * inv_f, cy_f = p.cy * inv_f;
     unsigned short* wl = sm.wlist[warp_id];
-    int staged_frame = -1;
+    constexpr uint32_t TABLE_BYTES = (uint32_t)(sizeof(CellRec) * DSAC_N_CONST);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&sm.mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&sm.mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int cur = 0;
+    int frame_in[2] = {-1, -1};          // frame whose table buffer b holds (or is receiving)
+    uint32_t parity[2] = {0u, 0u};
+    bool pending[2] = {false, false};    // a copy into buffer b has been issued and not yet waited for
     unsigned long long n_flagged = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t it = q.wq[item];
-        const int slot = (int)(it >> 6), chunk = (int)(it & 63u);
-        const int frame = slot / p.T;
-        if (frame != staged_frame) {   // the frame's cell table (38.4 KB) to shared memory
-            __syncthreads();
-            const uint4* src = reinterpret_cast<const uint4*>(q.celltab + (size_t)frame * DSAC_N_CONST);
-            uint4* dst = reinterpret_cast<uint4*>(sm.cell);
-            for (int k = tid; k < (int)(sizeof(CellRec) * DSAC_N_CONST / 16); k += K1F_THREADS) dst[k] = __ldg(src + k);
-            staged_frame = frame;
-            __syncthreads();
+    int item = blockIdx.x;
+    if (item < n_items) {
+        const int f0 = (int)(wq[item].x >> 7) / p.T;
+        if (tid == 0) tma_load_1d(sm.cell[0], q.celltab + (size_t)f0 * DSAC_N_CONST, TABLE_BYTES, &sm.mbar[0]);
+        frame_in[0] = f0;
+        pending[0] = true;
+    }
+    for (; item < n_items; item += gridDim.x) {
+        const uint2 it2 = wq[item];
+        const uint32_t it = it2.x;
+        const int slot = (int)(it >> 7), chunk = (int)(it & 127u);
+        const int frame = slot / p.T;           // == frame_in[cur]
+        // the next item's table, into the other buffer (free: everybody left it at the last switch)
+        const int nxt = item + gridDim.x;
+        int nframe = frame;
+        if (nxt < n_items) {
+            nframe = (int)(wq[nxt].x >> 7) / p.T;
+            if (nframe != frame && frame_in[cur ^ 1] != nframe) {
+                if (tid == 0) tma_load_1d(sm.cell[cur ^ 1], q.celltab + (size_t)nframe * DSAC_N_CONST, TABLE_BYTES, &sm.mbar[cur ^ 1]);
+                frame_in[cur ^ 1] = nframe;
+                pending[cur ^ 1] = true;
+            }
         }
-        const int n_round = q.state[slot].n_round;
+        if (pending[cur]) {
+            mbar_wait(&sm.mbar[cur], parity[cur]);
+            parity[cur] ^= 1u;
+            pending[cur] = false;
+        }
+        const CellRec* cell = sm.cell[cur];
         const int base = chunk * q.chunk;
-        const int n_here = min(q.chunk, n_round - base);
+        const int n_here = (int)it2.y;
         const uint2* cc = q.cells + (size_t)slot * q.cap + base;
         int cnt = 0;
         int i = warp_id * 32 + lane;
@@ -548,7 +640,7 @@ __global__ void __launch_bounds__(K1F_THREADS, K1F_MIN_BLOCKS) k1_filter(K1Split
             bool need = false;
             if (i < n_here) {
                 const int cells[4] = {(int)(c.x & 0xffffu), (int)(c.x >> 16), (int)(c.y & 0xffffu), (int)(c.y >> 16)};
-                need = k1_filter_candidate(sm.cell, cells, p.f, p.cx, p.cy, inv_f, cx_f, cy_f, (double)p.thr);
+                need = k1_filter_candidate(cell, cells, p.f, p.cx, p.cy, inv_f, cx_f, cy_f, (double)p.thr);
             }
             const uint32_t bits = __ballot_sync(0xffffffffu, need);
             if (need) wl[cnt + __popc(bits & ((1u << lane) - 1u))] = (unsigned short)(base + i);
@@ -558,27 +650,31 @@ __global__ void __launch_bounds__(K1F_THREADS, K1F_MIN_BLOCKS) k1_filter(K1Split
         __syncwarp();
         if (cnt > 0) {
             int at = 0;
-            if (lane == 0) at = atomicAdd(q.fq_n + q.round, cnt);
+            if (lane == 0) at = atomicAdd(q.fq_n + q.qidx, cnt);
             at = __shfl_sync(0xffffffffu, at, 0);
-            for (int k = lane; k < cnt; k += 32) q.fq[at + k] = ((uint32_t)slot << 14) | (uint32_t)wl[k];
+            for (int k = lane; k < cnt; k += 32) q.fq[at + k] = ((uint32_t)slot << K1S_IDX_BITS) | (uint32_t)wl[k];
             n_flagged += (unsigned long long)cnt;
         }
         __syncwarp();
+        if (nframe != frame) {   // moving to the other buffer: the one left behind may be overwritten from the next iteration on
+            __syncthreads();
+            cur ^= 1;
+        }
     }
     if (q.dbg && lane == 0 && n_flagged) atomicAdd(q.dbg + (size_t)q.round * 4 + 2, n_flagged);
 }
 
-// ------------------------------------------------------------------ k1_solve
-// Full fp64 P3P + the reference's reprojection check (cnn_softam.h:1041-1059) on the flagged candidates; 4 lanes per
-// candidate, lane `sub` handles quartic root `sub` (as phase D of k_sample).
 #ifndef K1V_GROUP
-#define K1V_GROUP 4   /* lanes per flagged candidate: 4 = one quartic root per lane, 2 = two roots per lane, 1 = one thread per candidate */
+#define K1V_GROUP 1   /* lanes per flagged candidate: 4 = one quartic root per lane, 2 = two roots per lane, 1 = one thread per candidate */
 #endif
-__global__ void __launch_bounds__(K1V_THREADS) k1_solve(K1SplitParams q) {
+#ifndef K1V_MIN_BLOCKS
+#define K1V_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(K1V_THREADS, K1V_MIN_BLOCKS) k1_solve(K1SplitParams q) {
     const SampleParams& p = q.sp;
     const int tid = threadIdx.x;
     constexpr int GROUP = K1V_GROUP, GROUPS = K1V_THREADS / GROUP, ROOTS = 4 / GROUP;
-    const int n_q = q.fq_n[q.round];
+    const int n_q = q.fq_n[q.qidx];
     const int sub = tid % GROUP;
     for (int base = blockIdx.x * GROUPS; base < n_q; base += gridDim.x * GROUPS) {
         const int qi = base + tid / GROUP;
@@ -589,8 +685,8 @@ __global__ void __launch_bounds__(K1V_THREADS) k1_solve(K1SplitParams q) {
         int nsol = 0, slot = 0, ci = 0;
         if (qi < n_q) {
             const uint32_t ent = q.fq[qi];
-            slot = (int)(ent >> 14);
-            ci = (int)(ent & 16383u);
+            slot = (int)(ent >> K1S_IDX_BITS);
+            ci = (int)(ent & ((1u << K1S_IDX_BITS) - 1u));
             const int frame = slot / p.T;
             const uint2 c = q.cells[(size_t)slot * q.cap + ci];
             const int cells[4] = {(int)(c.x & 0xffffu), (int)(c.x >> 16), (int)(c.y & 0xffffu), (int)(c.y >> 16)};

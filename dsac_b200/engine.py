@@ -20,7 +20,7 @@ ST_SAMPLER_EXHAUSTED, ST_REFINE_ABORTED = 1, 2
 EXPORTS = [
     "dsac_default_config", "dsac_engine_create", "dsac_engine_destroy", "dsac_last_error", "dsac_engine_config",
     "dsac_forward", "dsac_forward_submit", "dsac_forward_wait", "dsac_forward_device", "dsac_fetch", "dsac_device_view_get", "dsac_set_stages",
-    "dsac_set_tail_split", "dsac_launch_count", "dsac_set_score_hook", "dsac_set_score_backward_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_gather_patches_device", "dsac_coords_from_prediction_device", "dsac_kabsch",
+    "dsac_set_tail_split", "dsac_launch_count", "dsac_sampler_profile", "dsac_sampler_profile_read", "dsac_set_score_hook", "dsac_set_score_backward_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_gather_patches_device", "dsac_coords_from_prediction_device", "dsac_kabsch",
     "dsac_stochastic_subsample",
     "dsac_synth_frames", "dsac_version",
 ]
@@ -105,6 +105,8 @@ def load(build_if_missing=True):
                                         C.c_void_p]
     lib.dsac_fetch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ForwardOut), C.c_void_p]
     lib.dsac_device_view_get.argtypes = [C.c_void_p, C.POINTER(DeviceView)]
+    lib.dsac_sampler_profile.argtypes = [C.c_void_p, C.c_int32]
+    lib.dsac_sampler_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dsac_set_stages.argtypes = [C.c_void_p, C.c_uint32]
     lib.dsac_set_tail_split.argtypes = [C.c_void_p, C.c_int32]
     lib.dsac_set_score_hook.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -269,6 +271,17 @@ class Engine:
 
     def set_stages(self, mask):
         self._check(self.lib.dsac_set_stages(self.h, mask))
+
+    def sampler_profile(self, enable=True):
+        self._check(self.lib.dsac_sampler_profile(self.h, int(enable)))
+
+    def sampler_profile_read(self):
+        """(ms[4], counts[4]) of the last profiled forward: generation+selection, filter, solve, tail; candidates, flagged,
+        accepted, rounds."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_uint64 * 4)()
+        self._check(self.lib.dsac_sampler_profile_read(self.h, ms, cnt))
+        return list(ms), [int(x) for x in cnt]
 
     def set_tail_split(self, mode):
         """0: off, 1: forward_device + blocking forward (default), 2: submitted passes too (scheduling only)."""

@@ -160,6 +160,15 @@ int dsac_set_tail_split(dsac_engine* e, int32_t mode);
 /* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
 int64_t dsac_launch_count(const dsac_engine* e);
 
+/* Measurement aid for the sampler (the round-based pipeline of sampler_split.cuh): with the profile on, the engine records
+ * a CUDA event after every sampler launch of a forward pass and counts the candidates per round.
+ * dsac_sampler_profile_read waits for the last pass and returns
+ *   ms[0..3]     device time in: generation + selection (k1_cells, k1_slot), conservative filter (k1_filter),
+ *                full P3P solve (k1_solve), resume tail (k_sample; normally an empty launch);
+ *   counts[0..3] candidates generated, candidates flagged by the filter, candidates accepted, rounds that had work. */
+int dsac_sampler_profile(dsac_engine* e, int32_t enable);
+int dsac_sampler_profile_read(dsac_engine* e, double ms[4], uint64_t counts[4]);
+
 /* Score seam: replaces forward(diffMaps, stateObj) (lua_calls.h:284-300; call site
  * cnn_softam.h:1072).  If set, the engine materialises the diffmaps and calls the hook with
  * DEVICE pointers instead of evaluating the closed-form soft-inlier score.

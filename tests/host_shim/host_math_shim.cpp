@@ -105,6 +105,14 @@ extern "C" void shim_filter_stats(const int16_t* coords, const int32_t* pix, uin
 }
 
 // guard counters of the fp64 conservative filter (only with -DDSAC_FILTER_STATS)
+extern "C" double shim_filter_fp32_maxdev() {
+#ifdef DSAC_FILTER_STATS
+    return dsac::g_filter_fp32_maxdev;
+#else
+    return -1.0;
+#endif
+}
+
 extern "C" void shim_filter_reasons(long long out[24]) {
 #ifdef DSAC_FILTER_STATS
     for (int k = 0; k < 24; k++) out[k] = dsac::g_filter_reason[k];

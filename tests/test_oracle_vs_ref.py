@@ -169,3 +169,24 @@ def test_oracle_matches_the_reference_fixtures(oracle):
             assert rel(ob.dloss_dobj, g["dloss_dobj"]) <= 1e-12
             assert rel(ob.score_grads, g["score_out_grads"]) <= 1e-10
             assert rel(ob.dloss_dref, g["dloss_dref"]) <= 1e-12 and rel(ob.dref_dhyp, g["dref_dhyp"]) <= 1e-12
+
+
+@live
+def test_pose_file_reader_equals_the_references(engine_mod, tmp_path):
+    """the host mirror's 7-Scenes pose reader (dsac_b200/host/read_data.cpp) against the
+    reference's own readData + Hypothesis(info) (core/read_data.cpp:69-133) on pose files with a scene offset."""
+    import subprocess
+    E = engine_mod
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "apps"), "-s", "host_selftest"])
+    coords, pix, gt_cv, gt_jp = E.synth_frames(5, traj=True)
+    d = str(tmp_path)
+    R.write_dataset(d, "test", gt_jp, translation=[0.5, -1.25, 2.0])
+    for i in range(5):
+        rel_path = os.path.join("test", "synth", "poses", "frame-%06d.pose.txt" % i)
+        Rg, tg = R.read_pose(d, rel_path)
+        out = subprocess.run([os.path.join(root, "apps", "host_selftest"), "pose", rel_path], cwd=d, capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0, out.stdout + out.stderr
+        v = np.array([float(x) for x in out.stdout.split()])
+        assert np.abs(v[:9] - Rg.reshape(-1)).max() <= 2e-7 and np.abs(v[9:] - tg).max() <= 1e-3   # float arithmetic on both sides
+        assert np.abs(v[:9] - gt_jp[i, :9]).max() <= 1e-6 and np.abs(v[9:] - gt_jp[i, 9:]).max() <= 5e-3

@@ -22,6 +22,8 @@ def main(nf=8, n=250000, extra=()):
                flag_pct=round(100 * tot[2] / tot[0], 3), accept_pct=round(100 * tot[1] / tot[0], 3), secs=round(time.time() - t0, 1)))
     rs = (C.c_longlong * 24)(); shim.shim_filter_reasons(rs)
     if rs[0] >= 0: print("guards fired:", {k: rs[k] for k in range(24) if rs[k]})
+    shim.shim_filter_fp32_maxdev.restype = C.c_double
+    if shim.shim_filter_fp32_maxdev() >= 0: print("largest |fp32 - fp64| pixel error of the 4th-point stage (well-conditioned roots): %.3g px" % shim.shim_filter_fp32_maxdev())
     os.remove(so)
     return tot
 

@@ -1,16 +1,17 @@
-# Final capture of a round (one gpurun call): GPU tests, bench line, ncu launch list of the bench, full ncu captures of
-# the forward kernels and of the upstream gather, compute-sanitizer.  Tag = $1 (default r01).
+# Final capture of a round (one gpurun call): GPU tests, bench line, reference arm, ncu launch list of the bench, full ncu
+# captures of the forward kernels, compute-sanitizer.  Tag = $1 (default r02).  Run from the repo root of the snapshot.
 set -x
-T=${1:-r01}
+T=${1:-r02}
 cd $GRAFT_REPO_ROOT
+export DSAC_SKIP_BUILD=1
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv,noheader; nproc
-timeout 600 python -m pytest tests -m gpu -q --timeout=300 -rf > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_line.json 2> gpurun_out/${T}_bench.err; tail -c 400 gpurun_out/${T}_bench_line.json; tail -3 gpurun_out/${T}_bench.err
+timeout 1500 python -m pytest tests -m gpu -q -s --timeout=900 -rf > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_line.json 2> gpurun_out/${T}_bench.err; tail -c 600 gpurun_out/${T}_bench_line.json; tail -3 gpurun_out/${T}_bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err; tail -c 300 gpurun_out/${T}_bench_reference.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${T}.csv python bench.py --steps 2 --warmup 3 > gpurun_out/${T}_ncu_bench.log 2>&1
-for k in k_score k_sample k_refine; do DSAC_TAIL_SPLIT=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -s 2 -f -o gpurun_out/${k}_${T} python tools/prof_driver.py > gpurun_out/ncu_$k.log 2>&1; done
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gather -c 1 -s 2 -f -o gpurun_out/k_gather_${T} python tools/gather_probe.py > gpurun_out/ncu_k_gather.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${T}.csv python bench.py --steps 2 --warmup 3 > gpurun_out/${T}_ncu_bench.log 2>&1
+# full captures: the steady-state pass is the second one (-s skips the first pass's launches of that kernel)
+for spec in "k1_filter 9" "k1_slot 10" "k1_solve 9" "k_score 1" "k_refine 1"; do set -- $spec; DSAC_K1_OVERLAP=0 REPS=2 timeout 400 ncu --set full --clock-control none --import-source on -k regex:$1 -c 1 -s $2 -f -o gpurun_out/${1}_${T} python tools/prof_driver.py > gpurun_out/ncu_$1.log 2>&1; tail -1 gpurun_out/ncu_$1.log; done
 for tool in memcheck racecheck initcheck; do NB=5 REPS=1 timeout 400 compute-sanitizer --tool $tool python tools/prof_driver.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY" | sed "s/^/$tool fwd (5 frames): /"; done > gpurun_out/sanitizer_${T}.txt 2>&1
 timeout 400 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_backward.py -m gpu -q -k "test_backward_matches_oracle or (dsac_variant_backward_matches_oracle and 16)" 2>&1 | grep -E "ERROR SUMMARY|passed|failed" | sed "s/^/memcheck backward + backward_dsac: /" >> gpurun_out/sanitizer_${T}.txt
 cat gpurun_out/sanitizer_${T}.txt
