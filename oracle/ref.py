@@ -167,3 +167,48 @@ def train_round(cfg, root, coords, args=()):
     rc = _lib("libref_train_softam.so").ref_train_softam_round(C.byref(cfg), root.encode(), _p(coords), len(args), a, _p(dloss), C.byref(loss), _p(sog))
     assert rc == 0, rc
     return dloss, loss.value, sog
+
+
+# ---------------------------------------------------------------- DSAC / RANSAC variant (core/cnn.h, test_ransac.cpp, train_ransac.cpp)
+class DsacOut(C.Structure):
+    _fields_ = [("hyp_rvec", C.c_void_p), ("hyp_tvec", C.c_void_p), ("img_idx", C.c_void_p), ("sf", C.c_void_p),
+                ("ref_pose", C.c_void_p), ("losses", C.c_void_p), ("inlier_maps", C.c_void_p),
+                ("entropy", C.c_double), ("expected_loss", C.c_double), ("rot_err", C.c_double), ("t_err", C.c_double),
+                ("hyp_idx", C.c_int32), ("correct", C.c_int32)]
+
+
+class ForwardDsac:
+    def __init__(self, cfg):
+        H = cfg.n_hyps
+        self.hyp_rvec = np.zeros((H, 3)); self.hyp_tvec = np.zeros((H, 3)); self.img_idx = np.zeros((H, 4), np.int32)
+        self.sf = np.zeros(H); self.ref_pose = np.zeros((H, 6)); self.losses = np.zeros(H); self.inlier_maps = np.zeros((H, N), np.int32)
+        self.raw = DsacOut()
+        for k in ("hyp_rvec", "hyp_tvec", "img_idx", "sf", "ref_pose", "losses", "inlier_maps"):
+            setattr(self.raw, k, _p(getattr(self, k)))
+
+    def __getattr__(self, k):
+        raw = self.__dict__.get("raw")
+        if raw is not None and k in ("entropy", "expected_loss", "rot_err", "t_err", "hyp_idx", "correct"):
+            return getattr(raw, k)
+        raise AttributeError(k)
+
+
+def forward_dsac(cfg, coords, gt_R, gt_t, random_draw=True):
+    """processImage of the DSAC variant (cnn.h:1028-1257) of the reference on one synthetic frame."""
+    coords = np.ascontiguousarray(coords, np.int16).reshape(N, 3)
+    gR = np.ascontiguousarray(gt_R, np.float64).reshape(9)
+    gt = np.ascontiguousarray(gt_t, np.float64).reshape(3)
+    out = ForwardDsac(cfg)
+    rc = _lib("libref_dsac.so").ref_dsac_forward(C.byref(cfg), int(random_draw), _p(coords), _p(gR), _p(gt), C.byref(out.raw))
+    assert rc == 0
+    return out
+
+
+def train_round_dsac(cfg, root, coords, args=()):
+    """One round of main() of the reference's train_ransac.cpp on the one-frame dataset in `root`: (dLoss_dObj [N,3], expected loss)."""
+    coords = np.ascontiguousarray(coords, np.int16).reshape(1, N, 3)
+    dloss = np.zeros((N, 3)); loss = C.c_double(0)
+    a = _argv(list(args))
+    rc = _lib("libref_train_dsac.so").ref_train_dsac_round(C.byref(cfg), root.encode(), _p(coords), len(args), a, _p(dloss), C.byref(loss))
+    assert rc == 0, rc
+    return dloss, loss.value

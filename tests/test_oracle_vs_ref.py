@@ -190,3 +190,39 @@ def test_pose_file_reader_equals_the_references(engine_mod, tmp_path):
         v = np.array([float(x) for x in out.stdout.split()])
         assert np.abs(v[:9] - Rg.reshape(-1)).max() <= 2e-7 and np.abs(v[9:] - tg).max() <= 1e-3   # float arithmetic on both sides
         assert np.abs(v[:9] - gt_jp[i, :9]).max() <= 1e-6 and np.abs(v[9:] - gt_jp[i, 9:]).max() <= 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ DSAC / RANSAC variant
+@live
+@pytest.mark.parametrize("T,H,g,random_draw", [(1, 64, 0, True), (1, 64, 3, False), (4, 32, 2, True)])
+def test_dsac_variant_forward_equals_reference_process_image(oracle, engine_mod, T, H, g, random_draw):
+    """processImage of core/cnn.h:1028-1257 (draw :102-126, refinement of every hypothesis :1155-1228, expectedMaxLoss
+    :137-151) by the reference's own code  <->  orc_forward_dsac."""
+    O, E = oracle, engine_mod
+    coords, pix, gt_cv, gt_jp = E.synth_frames(1, frame0=g, n_streams=T)
+    r = R.forward_dsac(R.config(n_hyps=H, n_threads=T, frame=g), coords[0], gt_jp[0, :9], gt_jp[0, 9:], random_draw)
+    o = O.forward_dsac(O.default_config(seed=1305 + g * T, n_hyps=H, n_streams=T), coords[0], pix[0], gt_jp[0, :9], gt_jp[0, 9:], random_draw)
+    assert np.array_equal(o.img_idx, r.img_idx) and o.hyp_idx == r.hyp_idx and o.correct == r.correct
+    assert np.array_equal(o.inlier_maps, r.inlier_maps)
+    assert rel(o.hyp_rvec, r.hyp_rvec) <= 1e-12 and rel(o.hyp_tvec, r.hyp_tvec) <= 1e-12
+    assert np.abs(o.sf - r.sf).max() <= 1e-12 and rel(o.ref_pose, r.ref_pose) <= 1e-12
+    assert np.abs(o.losses - r.losses).max() <= 1e-9 and abs(o.expected_loss - r.expected_loss) <= 1e-10
+    assert abs(o.rot_err - r.rot_err) <= 1e-9 and abs(o.t_err - r.t_err) <= 1e-9
+
+
+@live
+@pytest.mark.parametrize("T,H,g", [(1, 32, 1), (4, 48, 6)])
+def test_dsac_variant_gradient_equals_the_references_main(oracle, engine_mod, T, H, g):
+    """One round of main() of core/train_ransac.cpp (expectation of the loss: sum_h sf_h dLossMax dRefine_h + dSMScore,
+    lines 304-381) on a one-frame dataset  <->  orc_backward_dsac."""
+    O, E = oracle, engine_mod
+    coords, pix, gt_cv, gt_jp = E.synth_frames(1, frame0=g, n_streams=T)
+    with tempfile.TemporaryDirectory() as d:
+        R.write_dataset(d, "training", gt_jp)
+        Rg, tg = R.read_pose(d, os.path.join("training", "synth", "poses", "frame-000000.pose.txt"))
+        dl, loss = R.train_round_dsac(R.config(n_hyps=H, n_threads=T, frame=g), d, coords[0], args=("-rI", str(H)))
+    oc = O.default_config(seed=1305 + g * T, n_hyps=H, n_streams=T)
+    o = O.forward_dsac(oc, coords[0], pix[0], Rg, tg, True)
+    ob = O.backward_dsac(oc, coords[0], pix[0], Rg, tg, o)
+    assert abs(o.expected_loss - loss) <= 1e-10
+    assert rel(ob.dloss_dobj, dl) <= 1e-10 and np.abs(dl).max() > 0
