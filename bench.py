@@ -31,13 +31,14 @@ BYTES_M = BYTES_F + H * NPTS * 4                       # diffmap materialised (r
 FLOPS_PER_PAIR = 38
 # fp64 flop model of the sampler's conservative filter (one thread per candidate; DESIGN.md section 5, counted from
 # p3p_quick_core / quartic_roots_banded in pose_math.cuh with FMA = 2 flops, a Newton-refined reciprocal = 8, rsqrt = 11):
-#   set-up (triangle, quadrics, quartic coefficients, Ferrari + cubic Newton, world frame) ... 388 flops
-#   one root slot (Newton step on the two quadrics, positivity, 4th point by congruence) ..... 173 flops
+#   set-up (triangle, quadrics, quartic coefficients, Ferrari + cubic Newton, world frame) ... 388 fp64 flops
+#   one root slot: Newton step on the two quadrics + positivity ............................... 91 fp64 flops
+#                  4th point by congruence + pixel test (fp32 since round 2) ................. 78 fp32 flops
 # ALGORITHMIC work = set-up + the REAL roots of the quartic: 96.9 % of the candidates have two, 0.7 % four, 2.4 % none
-# (tools/filter_stats.py over 2 * 10^6 candidates of the benchmark frames) -> 1.97 root slots = 729 flops per candidate.
-# The kernel evaluates slots 0 and 1 in every lane and slots 2, 3 only in warps that hold a four-root candidate (one in
-# five): ~2.4 slots = 803 executed flops per candidate.
-FILTER_FLOPS_SETUP, FILTER_FLOPS_ROOT, FILTER_MEAN_ROOTS, FILTER_EXEC_SLOTS = 388, 173, 1.97, 2.4
+# (tools/filter_stats.py over 2 * 10^6 candidates of the benchmark frames) -> 1.97 root slots = 567 fp64 (+ 154 fp32)
+# flops per candidate.  The kernel evaluates slots 0 and 1 in every lane and slots 2, 3 only in warps that hold a
+# four-root candidate (one in five): ~2.4 slots = 606 executed fp64 flops per candidate.
+FILTER_FLOPS_SETUP, FILTER_FLOPS_ROOT, FILTER_FP32_ROOT, FILTER_MEAN_ROOTS, FILTER_EXEC_SLOTS = 388, 91, 78, 1.97, 2.4
 FP64_PEAK_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12       # 148 SMs x 64 FMA/clk x 2 x 1.965 GHz = 37.2 (B200 non-tensor fp64)
 
 
@@ -400,6 +401,7 @@ def main():
                 "achieved": flops_alg / filt_s / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": flops_alg / filt_s / 1e12 / FP64_PEAK_TFLOPS,
                 "traffic": None, "peak_source": "148 SMs x 64 fp64 FMA/clk x 2 x 1.965 GHz (no measured fp64 peak in MEASURED_PEAKS.json)",
                 "algorithmic_flops_per_candidate": FILTER_FLOPS_SETUP + FILTER_MEAN_ROOTS * FILTER_FLOPS_ROOT,
+                "fp32_flops_per_candidate_beside": FILTER_MEAN_ROOTS * FILTER_FP32_ROOT,
                 "executed_flops_per_candidate": FILTER_FLOPS_SETUP + FILTER_EXEC_SLOTS * FILTER_FLOPS_ROOT, "executed_frac": flops_exec / filt_s / 1e12 / FP64_PEAK_TFLOPS,
                 "candidates_per_launch_set": k1_cnt[0], "ms_per_step": k1_ms[1], "share_of_step": k1_ms[1] / ssum}
     roofline_hbm = {"kernel": "k_score<write_diffmaps=1> (HxN reprojection-error matrix + soft-inlier score + soft-argmax tail)",

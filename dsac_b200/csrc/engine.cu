@@ -98,7 +98,7 @@ struct dsac_engine {
     int tail_split = 1;
     // split sampler (sampler_split.cuh): per-stream state and round buffers, sized at creation
     int k1_mode = 1;                // 1: round-based pipeline of flat kernels; 0: monolithic k_sample (DSAC_K1_MODE=mono)
-    int k1_rounds = 4, k1_cap = 0;
+    int k1_rounds = 5, k1_cap = 0;
     int k1_filter_grid = 0, k1_solve_grid = 0;
     unsigned long long k1_calls = 0;
     K1SlotState* d_k1_state = nullptr;
@@ -579,7 +579,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                 const bool portioned = n_slots >= 128 && r < 2;
                 const int sets = portioned ? (r == 0 ? 4 : 2) : 1;
                 q.round = r;
-                q.portion = portioned ? portion4 : e->k1_cap;
+                q.portion = portioned ? (r == 0 ? portion4 : 2 * portion4) : e->k1_cap;   // round 1 may use the whole capacity too
                 q.round_limit = q.portion * sets;
                 const int fgrid = (int)std::min<long long>(e->k1_filter_grid, n_slots * ((q.portion + q.chunk - 1) / q.chunk));
                 if (overlap && r > 0) CU(cudaStreamWaitEvent(stream, e->k1_ev_round, 0));   // the selection needs the previous round's solves

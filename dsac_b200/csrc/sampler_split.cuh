@@ -123,7 +123,9 @@ struct K1GSmem {
 __device__ __forceinline__ int k1_round_size(int quota, int acc, long long cand_base, int cap, long long cand_left, double prior_cpa) {
     double n;
     if (cand_base == 0) {
-        n = (prior_cpa > 0) ? K1S_FIRST_ROUND_FRAC * prior_cpa * quota : 16.0 * quota;
+        // no previous call to learn from: assume 64 candidates per accepted hypothesis (a wrong guess costs the first call
+        // some extra candidates or an extra round, never a different result)
+        n = K1S_FIRST_ROUND_FRAC * ((prior_cpa > 0) ? prior_cpa : 64.0) * quota;
         if (n < 64) n = 64;
     } else if (acc == 0) {
         n = 4.0 * (double)cand_base;

@@ -170,10 +170,10 @@ def test_score_hook_seam(engine_mod, oracle):
         class _W:
             def __init__(self, ptr, shape, typestr):
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
-        d = torch.as_tensor(_W(dm, (n, H, 1600), "<f4"), device="cuda")
-        s = torch.as_tensor(_W(sc, (n, H), "<f8"), device="cuda")
-        s.copy_(0.1 * torch.sigmoid(0.5 * (10.0 - d.double())).sum(2))
-        torch.cuda.synchronize()
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):   # the engine's stream: ordered after k_score, before the soft-argmax tail
+            d = torch.as_tensor(_W(dm, (n, H, 1600), "<f4"), device="cuda")
+            s = torch.as_tensor(_W(sc, (n, H), "<f8"), device="cuda")
+            s.copy_(0.1 * torch.sigmoid(0.5 * (10.0 - d.double())).sum(2))
         return 0
 
     eng.set_score_hook(hook)
