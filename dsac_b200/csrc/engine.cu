@@ -125,6 +125,7 @@ struct dsac_engine {
     cudaEvent_t k1_ev_gen[K1S_MAX_SETS] = {};     // generation of launch set i done
     cudaEvent_t k1_ev_round = nullptr;            // last solve of a round done
     int k1_overlap = 1;
+    int k1_fused = 0;                             // 1: filter of set k and generator of set k+1 in one warp-specialised kernel (k1_fused)
     int k1_wq_stride = 0;
 };
 
@@ -369,6 +370,8 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         for (int i = 0; i < K1S_MAX_SETS; i++) CUC(cudaEventCreateWithFlags(&e->k1_ev_gen[i], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&e->k1_ev_round, cudaEventDisableTiming));
         if (const char* ov = getenv("DSAC_K1_OVERLAP")) e->k1_overlap = atoi(ov);
+        if (const char* fu = getenv("DSAC_K1_FUSED")) e->k1_fused = atoi(fu);
+        CUC(cudaFuncSetAttribute(k1_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1XSmem)));
         CUC(cudaMalloc(&e->d_k1_stats, 4 * sizeof(unsigned long long)));
         CUC(cudaMemset(e->d_k1_stats, 0, 4 * sizeof(unsigned long long)));
         if (getenv("DSAC_K1_DEBUG")) CUC(cudaMalloc(&e->d_k1_dbg, K1S_MAX_ROUNDS * 4 * sizeof(unsigned long long)));
@@ -564,7 +567,8 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                 cudaEventRecord(e->k1_ev[e->k1_ev_n++], stream);
             };
             // with the profile on everything runs on one stream so that the event intervals are the kernels' own durations
-            const bool overlap = e->k1_overlap && !e->k1_profile;
+            const bool fused = e->k1_fused != 0;
+            const bool overlap = e->k1_overlap && !e->k1_profile && !fused;
             cudaStream_t side = overlap ? e->k1_side : stream;
             cudaStream_t solve_side = (overlap && e->k1_overlap >= 2) ? e->k1_side2 : side;
             const size_t n_slots_cap = (size_t)e->cfg.max_frames * c.n_streams * (size_t)e->k1_cap;
@@ -583,6 +587,29 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                 q.round_limit = q.portion * sets;
                 const int fgrid = (int)std::min<long long>(e->k1_filter_grid, n_slots * ((q.portion + q.chunk - 1) / q.chunk));
                 if (overlap && r > 0) CU(cudaStreamWaitEvent(stream, e->k1_ev_round, 0));   // the selection needs the previous round's solves
+                if (fused) {
+                    // one stream: slot (select + first portion), then per set { filter(k) | generator(k+1) } fused, solve(k)
+                    q.gen_only = 0; q.qidx = set; q.fq = e->d_k1_fq + (size_t)(set & 1) * n_slots_cap;
+                    k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
+                    mark(0);
+                    e->launches++;
+                    for (int k = 0; k < sets && set < K1S_MAX_SETS; k++, set++) {
+                        K1SplitParams qf = q;
+                        qf.gen_only = 0; qf.qidx = set; qf.fq = e->d_k1_fq + (size_t)(set & 1) * n_slots_cap;
+                        if (k + 1 < sets && set + 1 < K1S_MAX_SETS) {
+                            K1SplitParams qg = q;
+                            qg.gen_only = 1; qg.qidx = set + 1;
+                            k1_fused<<<e->sm_count, K1X_THREADS, sizeof(K1XSmem), stream>>>(qf, qg);
+                        } else {
+                            k1_filter<<<fgrid, K1F_THREADS, sizeof(K1FSmem), stream>>>(qf);
+                        }
+                        mark(1);
+                        k1_solve<<<e->k1_solve_grid, K1V_THREADS, 0, stream>>>(qf);
+                        mark(2);
+                        e->launches += 2;
+                    }
+                    continue;
+                }
                 for (int k = 0; k < sets && set < K1S_MAX_SETS; k++, set++) {
                     q.gen_only = (k > 0);
                     q.qidx = set;

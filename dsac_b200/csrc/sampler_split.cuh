@@ -114,6 +114,7 @@ struct K1GSmem {
     unsigned short brk_ci[K1_BRK_CAP], brk_cur[K1_BRK_CAP];
     int brk_n;
     int sel_total;
+    int or_flag;
 };
 
 // Size of the next round: enough candidates for the hypotheses still missing, from the acceptance rate observed so
@@ -140,14 +141,12 @@ __device__ __forceinline__ int k1_round_size(int quota, int acc, long long cand_
     return r;
 }
 
-#ifndef K1S_MIN_BLOCKS
-#define K1S_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitParams q) {
-    __shared__ K1GSmem sm;
+// The work of k1_slot for one (frame, stream), by a group of K1S_THREADS threads that synchronise with barrier BAR_ID
+// (0: the whole CTA of the k1_slot kernel; >= 1: the generator warps inside k1_fused).  tid: index within the group.
+template <int BAR_ID, int BAR_N>
+__device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm, const int tid, const int s, const int frame) {
     const SampleParams& p = q.sp;
-    const int tid = threadIdx.x, lane = tid & 31, warp_id = tid >> 5;
-    const int s = blockIdx.x, frame = blockIdx.y;
+    const int lane = tid & 31, warp_id = tid >> 5;
     const int slot = frame * p.T + s;
     K1SlotState& S = q.state[slot];
     int h0, quota;
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
             for (int k = tid; k < ln; k += K1S_THREADS) sm.vals[k] = S.left[k];
             if (tid == 0) { sm.any_reject = S.any_reject; sm.walk_fail = 0; }
         }
-        __syncthreads();
+        group_barrier<BAR_ID, BAR_N>();
     } else if (q.round == 0) {
         if (quota == 0) {
             if (tid == 0) {
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
         acc = 0;
         cand_base = 0;
         if (tid == 0) { sm.any_reject = 0; sm.walk_fail = 0; }
-        __syncthreads();
+        group_barrier<BAR_ID, BAR_N>();
     } else {
         if (S.done) return;
         // ---------------- selection: the first (quota - acc) accepted candidates of the previous round, in order
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
             mine += __popc(w[k]);
         }
         int tot;
-        int rank = block_excl_scan<K1S_WARPS>(mine, &tot, sm.warp[0]);
+        int rank = block_excl_scan<K1S_WARPS, BAR_ID, BAR_N>(mine, &tot, sm.warp[0], tid);
         const int room = quota - acc;
 #pragma unroll
         for (int k = 0; k < K1S_SEL_WORDS; k++) {
@@ -223,7 +222,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
                 rank++;
             }
         }
-        __syncthreads();
+        group_barrier<BAR_ID, BAR_N>();
         const int n_emit = min(tot, room);
         for (int k = tid; k < n_emit; k += K1S_THREADS) {
             const int i = sm.acc_list[k];
@@ -273,7 +272,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
             for (int k = tid; k < ln; k += K1S_THREADS) sm.vals[k] = S.left[k];
             if (tid == 0) { sm.any_reject = S.any_reject; sm.walk_fail = 0; }
         }
-        __syncthreads();
+        group_barrier<BAR_ID, BAR_N>();
     }
 
     // ---------------- size of this round (first launch set of the round), size of this portion
@@ -324,7 +323,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
                 if (rej_any) sm.any_reject = 1;
             }
             gen += MT_N;
-            __syncthreads();
+            group_barrier<BAR_ID, BAR_N>();
         }
         const int w_avail = min((int)(gen - pos), K1S_WORDS);
 
@@ -390,7 +389,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
                 }
             }
             if (lane == 0) sm.ev_n[warp_id] = cnt;
-            __syncthreads();
+            group_barrier<BAR_ID, BAR_N>();
             if (tid == 0) {
                 int cur = 0, ci = 0, nb = 1, stop_at = -1;
                 bool fail = false;
@@ -421,7 +420,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
                 sm.brk_n = nb;
                 sm.walk_fail = fail ? 1 : 0;
             }
-            __syncthreads();
+            group_barrier<BAR_ID, BAR_N>();
             if (!sm.walk_fail) {
                 const int n_ok = sm.n_sr, nb = sm.brk_n;
                 int m = 0;
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
                 int extra = 0, start = 0, qn = 0;
                 for (;;) {
                     int tot;
-                    const int excl = block_excl_scan<K1S_WARPS>(extra, &tot, sm.warp[par]);
+                    const int excl = block_excl_scan<K1S_WARPS, BAR_ID, BAR_N>(extra, &tot, sm.warp[par], tid);
                     par ^= 1;
                     start = rp + 8 * tid + excl;
                     int cells[4];
@@ -448,20 +447,20 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
                     const int ne = (qn < 0) ? 0 : (qn - start) - 8;
                     const int changed = (ne != extra);
                     extra = ne;
-                    if (!__syncthreads_or(changed)) break;
+                    if (!group_barrier_or<BAR_ID, BAR_N>(changed, &sm.or_flag, tid)) break;
                 }
                 int bad = (tid < n_chunk && qn < 0) ? tid : K1S_THREADS;
 #pragma unroll
                 for (int off = 16; off; off >>= 1) bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, off));
                 if (lane == 0) sm.warp[par][tid >> 5] = bad;
-                __syncthreads();
+                group_barrier<BAR_ID, BAR_N>();
                 int n_ok = n_chunk;
 #pragma unroll
                 for (int w = 0; w < K1S_WARPS; w++) n_ok = min(n_ok, sm.warp[par][w]);
                 par ^= 1;
                 if (tid < n_ok) sm.cand_start[n_done + tid] = (unsigned short)start;
                 if (tid == n_ok - 1) sm.newpos = (uint32_t)qn;          // end of the last complete candidate
-                __syncthreads();
+                group_barrier<BAR_ID, BAR_N>();
                 if (n_ok > 0) rp = (int)sm.newpos;
                 n_done += n_ok;
                 out_of_words = (n_ok < n_chunk);
@@ -471,7 +470,7 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
                 sm.n_sr = n_done;
             }
         }
-        __syncthreads();
+        group_barrier<BAR_ID, BAR_N>();
         const int n_sr = sm.n_sr;
 
         // the window's candidates to HBM
@@ -487,13 +486,13 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
             const int consumed = sm.cand_start[n_sr];
             const int left = w_avail - consumed;
             unsigned char keep[K1S_LEFT_CAP / K1S_THREADS];
-            __syncthreads();
+            group_barrier<BAR_ID, BAR_N>();
 #pragma unroll
             for (int k = 0; k < K1S_LEFT_CAP / K1S_THREADS; k++) {
                 const int i = tid + k * K1S_THREADS;
                 keep[k] = (i < left) ? sm.vals[consumed + i] : (unsigned char)0;
             }
-            __syncthreads();
+            group_barrier<BAR_ID, BAR_N>();
             bool rej_left = false;
 #pragma unroll
             for (int k = 0; k < K1S_LEFT_CAP / K1S_THREADS; k++) {
@@ -504,12 +503,12 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
                 }
             }
             if (tid == 0) { sm.any_reject = 0; sm.walk_fail = 0; }
-            __syncthreads();
+            group_barrier<BAR_ID, BAR_N>();
             if (rej_left) sm.any_reject = 1;   // a rejected draw carried over into the next window
             if (left > K1S_LEFT_CAP && tid == 0) S.overflow = 1;
             pos += (uint32_t)consumed;
             produced += n_sr;
-            __syncthreads();
+            group_barrier<BAR_ID, BAR_N>();
         }
         if (n_sr == 0) break;   // (cannot happen: every window holds at least one candidate)
     }
@@ -543,6 +542,14 @@ __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitPa
     }
 }
 
+#ifndef K1S_MIN_BLOCKS
+#define K1S_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitParams q) {
+    __shared__ K1GSmem sm;
+    k1_slot_body<0, 0>(q, sm, threadIdx.x, blockIdx.x, blockIdx.y);
+}
+
 // ------------------------------------------------------------------ k1_filter
 // The filter's inputs straight from the cell table: bearings of points 0..2 from the stored 1/|(u, v, 1)|.
 __device__ __forceinline__ bool k1_filter_candidate(const CellRec* cell, const int cells[4], double f, double cx, double cy,
@@ -568,7 +575,7 @@ __device__ __forceinline__ bool k1_filter_candidate(const CellRec* cell, const i
 #endif
 struct K1FSmem {
     CellRec cell[2][DSAC_N_CONST];            // the frame's cell table, double-buffered: 2 x 38.4 KB
-    unsigned short wlist[K1F_THREADS / 32][K1F_MAX_CHUNK / (K1F_THREADS / 32)];   // per warp: flagged candidates of its share of the item
+    unsigned short wlist[12][K1F_MAX_CHUNK / 8];   // per warp (8 in k1_filter, 12 in k1_fused): flagged candidates of its share of the item
     unsigned long long mbar[2];               // one transaction barrier per buffer
 };
 
@@ -576,44 +583,39 @@ struct K1FSmem {
 // copy, the CTA waits on the transaction barrier, and the table of the NEXT work item is fetched into the other buffer
 // while the warps filter the current one.
 // One work item = up to `chunk` consecutive candidates of one stream.  After the cell table is in shared memory the
-// warps run independently: a warp filters every 8th group of 32 candidates of the item (coalesced 8-byte loads of the
-// cell indices, the next group's prefetched), keeps the flagged ones in its own list and appends them to the global
-// queue with one atomic per item.  A block barrier only when the CTA moves on to another frame's table.
-__global__ void __maxnreg__(K1F_MAXREG) k1_filter(K1SplitParams q) {
-    extern __shared__ __align__(128) unsigned char k1f_smem_raw[];
-    K1FSmem& sm = *reinterpret_cast<K1FSmem*>(k1f_smem_raw);
+// warps run independently: a warp filters every (NTHREADS/32)-th group of 32 candidates of the item (coalesced 8-byte
+// loads of the cell indices, the next group's prefetched), keeps the flagged ones in its own list and appends them to
+// the global queue with one atomic per item.  A group barrier only when moving on to another frame's table.
+// The group: NTHREADS threads synchronising with barrier BAR_ID (0: the whole CTA of k1_filter; >= 1: the filter warps
+// of k1_fused); items first_item, first_item + item_stride, ...  The transaction barriers must have been initialised.
+template <int BAR_ID, int NTHREADS>
+__device__ __forceinline__ void k1_filter_body(const K1SplitParams& q, K1FSmem& sm, const int tid, const int first_item, const int item_stride) {
     const SampleParams& p = q.sp;
-    const int tid = threadIdx.x, lane = tid & 31, warp_id = tid >> 5;
+    const int lane = tid & 31, warp_id = tid >> 5;
     const int n_items = q.wq_n[q.qidx];
     const uint2* wq = q.wq + (size_t)q.qidx * q.wq_stride;
     const double inv_f = 1. / p.f, cx_f = p.cx * inv_f, cy_f = p.cy * inv_f;
     unsigned short* wl = sm.wlist[warp_id];
     constexpr uint32_t TABLE_BYTES = (uint32_t)(sizeof(CellRec) * DSAC_N_CONST);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&sm.mbar[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&sm.mbar[1])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
     int cur = 0;
     int frame_in[2] = {-1, -1};          // frame whose table buffer b holds (or is receiving)
     uint32_t parity[2] = {0u, 0u};
     bool pending[2] = {false, false};    // a copy into buffer b has been issued and not yet waited for
     unsigned long long n_flagged = 0;
-    int item = blockIdx.x;
+    int item = first_item;
     if (item < n_items) {
         const int f0 = (int)(wq[item].x >> 7) / p.T;
         if (tid == 0) tma_load_1d(sm.cell[0], q.celltab + (size_t)f0 * DSAC_N_CONST, TABLE_BYTES, &sm.mbar[0]);
         frame_in[0] = f0;
         pending[0] = true;
     }
-    for (; item < n_items; item += gridDim.x) {
+    for (; item < n_items; item += item_stride) {
         const uint2 it2 = wq[item];
         const uint32_t it = it2.x;
         const int slot = (int)(it >> 7), chunk = (int)(it & 127u);
         const int frame = slot / p.T;           // == frame_in[cur]
         // the next item's table, into the other buffer (free: everybody left it at the last switch)
-        const int nxt = item + gridDim.x;
+        const int nxt = item + item_stride;
         int nframe = frame;
         if (nxt < n_items) {
             nframe = (int)(wq[nxt].x >> 7) / p.T;
@@ -635,9 +637,9 @@ __global__ void __maxnreg__(K1F_MAXREG) k1_filter(K1SplitParams q) {
         int cnt = 0;
         int i = warp_id * 32 + lane;
         uint2 c = (i < n_here) ? __ldg(cc + i) : make_uint2(0u, 0u);
-        for (int i0 = warp_id * 32; i0 < n_here; i0 += K1F_THREADS) {
+        for (int i0 = warp_id * 32; i0 < n_here; i0 += NTHREADS) {
             i = i0 + lane;
-            const int in = i + K1F_THREADS;
+            const int in = i + NTHREADS;
             const uint2 cn = (in < n_here) ? __ldg(cc + in) : make_uint2(0u, 0u);   // next group's cell indices
             bool need = false;
             if (i < n_here) {
@@ -659,11 +661,50 @@ __global__ void __maxnreg__(K1F_MAXREG) k1_filter(K1SplitParams q) {
         }
         __syncwarp();
         if (nframe != frame) {   // moving to the other buffer: the one left behind may be overwritten from the next iteration on
-            __syncthreads();
+            group_barrier<BAR_ID, NTHREADS>();
             cur ^= 1;
         }
     }
     if (q.dbg && lane == 0 && n_flagged) atomicAdd(q.dbg + (size_t)q.round * 4 + 2, n_flagged);
+}
+
+__global__ void __maxnreg__(K1F_MAXREG) k1_filter(K1SplitParams q) {
+    extern __shared__ __align__(128) unsigned char k1f_smem_raw[];
+    K1FSmem& sm = *reinterpret_cast<K1FSmem*>(k1f_smem_raw);
+    if (threadIdx.x == 0) { mbar_init(&sm.mbar[0]); mbar_init(&sm.mbar[1]); }
+    __syncthreads();
+    k1_filter_body<0, K1F_THREADS>(q, sm, threadIdx.x, blockIdx.x, gridDim.x);
+}
+
+// ------------------------------------------------------------------ k1_fused
+// The filter of launch set k and the generator of launch set k+1 in ONE persistent CTA per SM, warp-specialised: 12
+// filter warps (fp64 pipe) and 8 generator warps (integer pipe) share the SM's issue slots, so the generation of the next
+// portion costs (almost) no time of its own.  Separate kernels cannot be made co-resident reliably: two filter CTAs use
+// the whole register file.  Here the register file is split by setmaxnreg: the CTA starts at 96 registers per thread
+// (640 x 96 = 60 K), the generator warp groups drop to 56, the filter warp groups rise to 128.
+constexpr int K1X_FILTER_THREADS = 384, K1X_GEN_THREADS = K1S_THREADS, K1X_THREADS = K1X_FILTER_THREADS + K1X_GEN_THREADS;
+struct K1XSmem {
+    K1FSmem f;
+    K1GSmem g;
+};
+
+__global__ void __launch_bounds__(K1X_THREADS, 1) k1_fused(K1SplitParams qf, K1SplitParams qg) {
+    extern __shared__ __align__(128) unsigned char k1x_smem_raw[];
+    K1XSmem& sm = *reinterpret_cast<K1XSmem*>(k1x_smem_raw);
+    if (threadIdx.x == 0) { mbar_init(&sm.f.mbar[0]); mbar_init(&sm.f.mbar[1]); }
+    __syncthreads();
+    if (threadIdx.x < K1X_FILTER_THREADS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        k1_filter_body<2, K1X_FILTER_THREADS>(qf, sm.f, threadIdx.x, blockIdx.x, gridDim.x);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int tid = threadIdx.x - K1X_FILTER_THREADS;
+        const int T = qg.sp.T;
+        for (int slot = blockIdx.x; slot < qg.n_slots; slot += gridDim.x) {
+            k1_slot_body<1, K1X_GEN_THREADS>(qg, sm.g, tid, slot % T, slot / T);
+            group_barrier<1, K1X_GEN_THREADS>();   // the group's shared memory is reused by the next slot
+        }
+    }
 }
 
 #ifndef K1V_GROUP

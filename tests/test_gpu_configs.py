@@ -62,11 +62,13 @@ def test_config4_all_1024_frames_match_the_oracle(engine_mod, oracle):
         mx["ref_t"] = max(mx["ref_t"], np.abs(o.ref[3:] - res.ref_pose[f][3:]).max())
         mx["loss"] = max(mx["loss"], abs(o.loss - res.loss[f]))
     print("config 4, measured maxima over 1024 frames x 256 hypotheses:", {k: float("%.3g" % v) for k, v in mx.items()})
-    assert mx["rvec"] <= 1e-9 and mx["tvec"] <= 1e-6
-    assert mx["score_rel"] <= 2e-5 and mx["sf"] <= 1e-4        # measured 1.05e-5 / see BASELINE.md section 6
-    assert mx["avg_r"] <= 1e-4 and mx["avg_t"] <= 1e-1         # soft-argmax pose: rad / mm (propagated fp32 score error)
-    assert mx["ref_r"] <= 1e-6 and mx["ref_t"] <= 1e-3          # refined pose: far inside the 0.01 deg / 0.1 mm contract
-    assert mx["loss"] <= 1e-4
+    # asserted at ~5x the measured maxima (rvec 2.7e-10, tvec 3.9e-7, scores 1.05e-5, sf 4.1e-6,
+    # soft-argmax pose 6.4e-8 rad / 1.6e-4 mm, refined pose 1.3e-10 rad / 4.5e-7 mm, loss 3.0e-8)
+    assert mx["rvec"] <= 1e-9 and mx["tvec"] <= 2e-6
+    assert mx["score_rel"] <= 2e-5 and mx["sf"] <= 2e-5
+    assert mx["avg_r"] <= 1e-6 and mx["avg_t"] <= 2e-3         # soft-argmax pose: rad / mm (propagated fp32 score error)
+    assert mx["ref_r"] <= 1e-8 and mx["ref_t"] <= 1e-5          # refined pose: far inside the 0.01 deg / 0.1 mm contract
+    assert mx["loss"] <= 1e-6
 
 
 @pytest.mark.parametrize("fix_q4", [0, 1])
@@ -96,7 +98,7 @@ def test_config3_backward_at_256_hypotheses(engine_mod, oracle, fix_q4):
         assert rel(bw.score_grads[f], obw.score_grads, 1e-6) <= 1e-4
         worst = max(worst, rel(bw.dloss_dobj[f], obw.dloss_dobj, 1e-6))
     print("config 3 (H=256, fix_q4=%d): final gradient, max relative-to-max difference %.3g" % (fix_q4, worst))
-    assert worst <= 1e-3
+    assert worst <= 1e-4     # measured 9.3e-6: BASELINE.md's 1e-4-of-max contract holds at config 3's full size
 
 
 def test_config5_thousand_frame_sequence_logs(engine_mod, oracle, tmp_path):
@@ -155,7 +157,7 @@ def test_engine_matches_the_reference_fixtures(engine_mod):
         if "dloss_dobj" in g:
             bw = eng.backward(g["coords"][None], g["pix"][None], gt)
             d = np.abs(bw.dloss_dobj[0] - g["dloss_dobj"]).max() / np.abs(g["dloss_dobj"]).max()
-            assert d <= 1e-3, (name, d)
+            assert d <= 5e-3, (name, d)   # measured up to 1.0e-3 at H = 64 (few hypotheses carry the soft-argmax; 9e-6 at H = 256)
             # dLossMax at the GPU's refined pose vs at the reference's: the poses differ by <= 1e-6 rad (fp32 scores ->
             # soft-argmax -> refinement) and d(angle)/d(pose) carries a 1 / sin(angle) factor at sub-degree errors
             assert np.abs(bw.dloss_dref[0] - g["dloss_dref"]).max() <= 1e-3 * max(1.0, np.abs(g["dloss_dref"]).max())
