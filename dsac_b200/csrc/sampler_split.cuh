@@ -35,7 +35,10 @@ constexpr int K1S_MAX_CAP = 32768;               // candidates per stream and ro
 constexpr int K1S_IDX_BITS = 15;
 constexpr int K1S_SEL_WORDS = K1S_MAX_CAP / 32 / K1S_THREADS_DEF;   // accept-bit words per thread in the selection
 constexpr int K1S_ACC_LIST = 1024;               // accepted candidates selected per stream and round (<= quota <= DSAC_MAX_HYPS)
-constexpr int K1F_THREADS = 256;                 // k1_filter
+#ifndef K1F_THREADS_DEF
+#define K1F_THREADS_DEF 256
+#endif
+constexpr int K1F_THREADS = K1F_THREADS_DEF;     // k1_filter
 constexpr int K1F_MAX_CHUNK = 2048;              // candidates per filter work item (multiple of K1F_THREADS)
 constexpr int K1V_THREADS = 128;                 // k1_solve: 32 groups of 4 lanes
 constexpr int K1S_MAX_ROUNDS = 16;
@@ -682,6 +685,15 @@ __global__ void __maxnreg__(K1F_MAXREG) k1_filter(K1SplitParams q) {
 // portion costs (almost) no time of its own.  Separate kernels cannot be made co-resident reliably: two filter CTAs use
 // the whole register file.  Here the register file is split by setmaxnreg: the CTA starts at 96 registers per thread
 // (640 x 96 = 60 K), the generator warp groups drop to 56, the filter warp groups rise to 128.
+#ifndef K1X_FILTER_REGS
+#define K1X_FILTER_REGS 128
+#endif
+#ifndef K1X_GEN_REGS
+#define K1X_GEN_REGS 48
+#endif
+// the CTA's register pool is what it was launched with (640 threads x 96); after the split it must hold
+// 384 x K1X_FILTER_REGS + 256 x K1X_GEN_REGS, or setmaxnreg.inc waits for ever
+static_assert(384 * K1X_FILTER_REGS + 256 * K1X_GEN_REGS <= 640 * 96, "k1_fused: register split exceeds the launch allocation");
 constexpr int K1X_FILTER_THREADS = 384, K1X_GEN_THREADS = K1S_THREADS, K1X_THREADS = K1X_FILTER_THREADS + K1X_GEN_THREADS;
 struct K1XSmem {
     K1FSmem f;
@@ -694,10 +706,10 @@ __global__ void __launch_bounds__(K1X_THREADS, 1) k1_fused(K1SplitParams qf, K1S
     if (threadIdx.x == 0) { mbar_init(&sm.f.mbar[0]); mbar_init(&sm.f.mbar[1]); }
     __syncthreads();
     if (threadIdx.x < K1X_FILTER_THREADS) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K1X_FILTER_REGS));
         k1_filter_body<2, K1X_FILTER_THREADS>(qf, sm.f, threadIdx.x, blockIdx.x, gridDim.x);
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K1X_GEN_REGS));
         const int tid = threadIdx.x - K1X_FILTER_THREADS;
         const int T = qg.sp.T;
         for (int slot = blockIdx.x; slot < qg.n_slots; slot += gridDim.x) {

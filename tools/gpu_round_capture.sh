@@ -10,8 +10,13 @@ timeout 1500 python -m pytest tests -m gpu -q -s --timeout=900 -rf > gpurun_out/
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_line.json 2> gpurun_out/${T}_bench.err; tail -c 600 gpurun_out/${T}_bench_line.json; tail -3 gpurun_out/${T}_bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err; tail -c 300 gpurun_out/${T}_bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${T}.csv python bench.py --steps 2 --warmup 3 > gpurun_out/${T}_ncu_bench.log 2>&1
-# full captures: the steady-state pass is the second one (-s skips the first pass's launches of that kernel)
-for spec in "k1_filter 9" "k1_slot 10" "k1_solve 9" "k_score 1" "k_refine 1"; do set -- $spec; DSAC_K1_OVERLAP=0 REPS=2 timeout 400 ncu --set full --clock-control none --import-source on -k regex:$1 -c 1 -s $2 -f -o gpurun_out/${1}_${T} python tools/prof_driver.py > gpurun_out/ncu_$1.log 2>&1; tail -1 gpurun_out/ncu_$1.log; done
+# full captures: the steady-state pass is the second one; the number of launches of each kernel in one pass (it depends on
+# the round / portion schedule) is counted from a one-pass launch list, and -s skips exactly the first pass
+DSAC_K1_OVERLAP=0 REPS=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_onepass.csv python tools/prof_driver.py > /dev/null 2>&1
+for k in k1_filter k1_slot k1_solve k_score k_refine; do
+  skip=$(grep -c "[ :\"]$k[<(]" gpurun_out/${T}_onepass.csv); echo "$k: $skip launches per pass"
+  DSAC_K1_OVERLAP=0 REPS=2 timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -s $skip -f -o gpurun_out/${k}_${T} python tools/prof_driver.py > gpurun_out/ncu_$k.log 2>&1; tail -1 gpurun_out/ncu_$k.log
+done
 for tool in memcheck racecheck initcheck; do NB=5 REPS=1 timeout 400 compute-sanitizer --tool $tool python tools/prof_driver.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY" | sed "s/^/$tool fwd (5 frames): /"; done > gpurun_out/sanitizer_${T}.txt 2>&1
 timeout 400 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_backward.py -m gpu -q -k "test_backward_matches_oracle or (dsac_variant_backward_matches_oracle and 16)" 2>&1 | grep -E "ERROR SUMMARY|passed|failed" | sed "s/^/memcheck backward + backward_dsac: /" >> gpurun_out/sanitizer_${T}.txt
 cat gpurun_out/sanitizer_${T}.txt
