@@ -99,6 +99,7 @@ struct dsac_engine {
     // split sampler (sampler_split.cuh): per-stream state and round buffers, sized at creation
     int k1_mode = 1;                // 1: round-based pipeline of flat kernels; 0: monolithic k_sample (DSAC_K1_MODE=mono)
     int k1_rounds = 5, k1_cap = 0;
+    bool k1_rounds_fixed = false;   // DSAC_K1_ROUNDS given
     int k1_filter_grid = 0, k1_solve_grid = 0;
     unsigned long long k1_calls = 0;
     K1SlotState* d_k1_state = nullptr;
@@ -337,11 +338,13 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
     }
     CUC(cudaMallocHost(&e->h_stream_ncand, n * cfg->n_streams * sizeof(long long)));
     if (const char* m = getenv("DSAC_K1_MODE")) e->k1_mode = (strcmp(m, "mono") == 0) ? 0 : 1;
-    if (const char* r = getenv("DSAC_K1_ROUNDS")) e->k1_rounds = std::max(1, std::min(K1S_MAX_ROUNDS - 1, atoi(r)));
+    if (const char* r = getenv("DSAC_K1_ROUNDS")) { e->k1_rounds = std::max(1, std::min(K1S_MAX_ROUNDS - 1, atoi(r))); e->k1_rounds_fixed = true; }
     if (e->k1_mode) {
         const size_t T = (size_t)cfg->n_streams, slots = n * T;
         const int quota_max = (cfg->n_hyps + cfg->n_streams - 1) / cfg->n_streams;
-        int cap = std::min(K1S_MAX_CAP, std::max(1024, K1S_CAP_PER_HYP * quota_max));
+        // few streams (single-frame latency): the first round takes 115 % of the expected need, so the capacity is larger
+        const int cap_per_hyp = slots < 128 ? (K1S_CAP_PER_HYP * 3) / 2 : K1S_CAP_PER_HYP;
+        int cap = std::min(K1S_MAX_CAP, std::max(1024, cap_per_hyp * quota_max));
         cap = (cap + 1023) & ~1023;     // a round is generated in portions of cap / 4, themselves multiples of 256
         e->k1_cap = cap;
         e->k1_wq_stride = (int)(slots * 128);
@@ -535,6 +538,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             q.wq = e->d_k1_wq; q.fq = e->d_k1_fq;
             q.wq_n = e->d_k1_counters; q.fq_n = e->d_k1_counters + K1S_MAX_SETS;
             q.wq_stride = e->k1_wq_stride;
+            q.first_frac = (double)K1S_FIRST_ROUND_FRAC;
             const int par = (int)(e->k1_calls & 1ull);
             e->k1_calls++;
             q.stats_cur = e->d_k1_stats + 2 * par; q.stats_prev = e->d_k1_stats + 2 * (par ^ 1);
@@ -577,7 +581,13 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             mark(0);
             e->launches++;
             int set = 0;
-            for (int r = 0; r < e->k1_rounds; r++) {
+            // few streams (single-frame latency): no previous call's shortfall to make up in later rounds -- the first round
+            // takes 115 % of the expected need and one top-up round follows (every round is three dependent launches);
+            // the rare straggler goes to the monolithic kernel
+            const bool few = n_slots < 128;
+            if (few) q.first_frac = 1.15;
+            const int n_rounds = (few && !e->k1_rounds_fixed) ? std::min(e->k1_rounds, 2) : e->k1_rounds;
+            for (int r = 0; r < n_rounds; r++) {
                 // portions only pay when the generator has the whole GPU to fill (many streams); a few streams (single-frame
                 // latency, BASELINE config 2) take every round in one launch set: fewer dependent launches
                 const bool portioned = n_slots >= 128 && r < 2;
@@ -635,7 +645,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                 if (overlap) CU(cudaEventRecord(e->k1_ev_round, solve_side));
             }
             if (overlap) CU(cudaStreamWaitEvent(stream, e->k1_ev_round, 0));
-            q.round = e->k1_rounds; q.select_only = 1; q.gen_only = 0;
+            q.round = n_rounds; q.select_only = 1; q.gen_only = 0;
             k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
             mark(0);
             sp.resume = q.state;   // streams the rounds left unfinished (normally none) continue in the monolithic kernel

@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_sample(SamplePara
 
     const K1SlotState* rs = p.resume ? p.resume + ((size_t)frame * p.T + s) : nullptr;
     if (rs && rs->done) return;
+    if (rs && rs->overflow) rs = nullptr;   // the leftover of a round did not fit the state (cannot happen with the window sizes used): redo the stream from its seed
     // stream s of global frame g: mt19937(seed + g*T + s)   (thread_rand.cpp:52 for g = 0)
     if (!rs && tid == 0) mt_seed(sm.st, p.seed + (uint32_t)((p.frame0 + frame) * (long long)p.T + s));
 

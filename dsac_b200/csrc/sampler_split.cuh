@@ -82,6 +82,7 @@ struct K1SplitParams {
     int round_limit;            // candidates a round may have at most (= portion * launch sets of the round)
     int qidx;                   // launch set of this call: index into wq_n / fq_n, wq region qidx * wq_stride
     int wq_stride;
+    double first_frac;          // first round: this fraction of the expected need (K1S_FIRST_ROUND_FRAC; > 1 for few streams)
 };
 
 // ------------------------------------------------------------------ k1_cells
@@ -124,12 +125,12 @@ struct K1GSmem {
 // far (cpa = candidates per accepted hypothesis) plus a margin of ~2.5 sigma of the binomial count, so that nearly
 // every stream finishes in the round.  The first round has no observation of its own: it takes 80 % of what the
 // streams of the previous call needed (prior), or 16 candidates per hypothesis.
-__device__ __forceinline__ int k1_round_size(int quota, int acc, long long cand_base, int cap, long long cand_left, double prior_cpa) {
+__device__ __forceinline__ int k1_round_size(int quota, int acc, long long cand_base, int cap, long long cand_left, double prior_cpa, double first_frac) {
     double n;
     if (cand_base == 0) {
         // no previous call to learn from: assume 64 candidates per accepted hypothesis (a wrong guess costs the first call
         // some extra candidates or an extra round, never a different result)
-        n = K1S_FIRST_ROUND_FRAC * ((prior_cpa > 0) ? prior_cpa : 64.0) * quota;
+        n = first_frac * ((prior_cpa > 0) ? prior_cpa : 64.0) * quota;
         if (n < 64) n = 64;
     } else if (acc == 0) {
         n = 4.0 * (double)cand_base;
@@ -285,7 +286,7 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
     } else {
         double prior = 0;
         if (q.stats_prev && q.stats_prev[1] > 0) prior = (double)q.stats_prev[0] / (double)q.stats_prev[1];
-        round_total = k1_round_size(quota, acc, cand_base, min(q.cap, q.round_limit), cand_max - cand_base, prior);
+        round_total = k1_round_size(quota, acc, cand_base, min(q.cap, q.round_limit), cand_max - cand_base, prior, q.first_frac);
     }
     const int n_round = min(q.portion, round_total - already);   // candidates this launch generates
 
