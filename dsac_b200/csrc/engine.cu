@@ -98,7 +98,7 @@ struct dsac_engine {
     int tail_split = 1;
     // split sampler (sampler_split.cuh): per-stream state and round buffers, sized at creation
     int k1_mode = 1;                // 1: round-based pipeline of flat kernels; 0: monolithic k_sample (DSAC_K1_MODE=mono)
-    int k1_rounds = 5, k1_cap = 0;
+    int k1_rounds = 3, k1_cap = 0;   // rounds 0..2 finish every stream of the benchmark batches; a straggler continues in k_sample (resume). 5 rounds = 6 empty launches per pass (measured +0.02 ms)
     bool k1_rounds_fixed = false;   // DSAC_K1_ROUNDS given
     int k1_filter_grid = 0, k1_solve_grid = 0;
     unsigned long long k1_calls = 0;
@@ -126,6 +126,7 @@ struct dsac_engine {
     cudaEvent_t k1_ev_gen[K1S_MAX_SETS] = {};     // generation of launch set i done
     cudaEvent_t k1_ev_round = nullptr;            // last solve of a round done
     int k1_overlap = 1;
+    int k1_solve_batch = 0;                       // 1: one k1_solve per round over the flagged candidates of all its launch sets (measured SLOWER, 3.07 vs 2.92 ms per step: a per-set solve runs beside the next set's generator, a per-round one runs alone)
     int k1_fused = 0;                             // 1: filter of set k and generator of set k+1 in one warp-specialised kernel (k1_fused)
     int k1_wq_stride = 0;
 };
@@ -374,6 +375,7 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         CUC(cudaEventCreateWithFlags(&e->k1_ev_round, cudaEventDisableTiming));
         if (const char* ov = getenv("DSAC_K1_OVERLAP")) e->k1_overlap = atoi(ov);
         if (const char* fu = getenv("DSAC_K1_FUSED")) e->k1_fused = atoi(fu);
+        if (const char* sb = getenv("DSAC_K1_SOLVE_BATCH")) e->k1_solve_batch = atoi(sb);
         CUC(cudaFuncSetAttribute(k1_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1XSmem)));
         CUC(cudaMalloc(&e->d_k1_stats, 4 * sizeof(unsigned long long)));
         CUC(cudaMemset(e->d_k1_stats, 0, 4 * sizeof(unsigned long long)));
@@ -577,7 +579,10 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             cudaStream_t solve_side = (overlap && e->k1_overlap >= 2) ? e->k1_side2 : side;
             const size_t n_slots_cap = (size_t)e->cfg.max_frames * c.n_streams * (size_t)e->k1_cap;
             mark(-1);
-            k1_cells<<<(unsigned)(((size_t)n * Nn + 255) / 256), 256, 0, stream>>>(q, n);
+            {
+                const int cell_blocks = (int)(((size_t)n * Nn + 255) / 256), seed_blocks = (int)((n_slots + 31) / 32);
+                k1_cells<<<(unsigned)(cell_blocks + seed_blocks), 256, 0, stream>>>(q, n, cell_blocks);
+            }
             mark(0);
             e->launches++;
             int set = 0;
@@ -599,16 +604,16 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                 if (overlap && r > 0) CU(cudaStreamWaitEvent(stream, e->k1_ev_round, 0));   // the selection needs the previous round's solves
                 if (fused) {
                     // one stream: slot (select + first portion), then per set { filter(k) | generator(k+1) } fused, solve(k)
-                    q.gen_only = 0; q.qidx = set; q.fq = e->d_k1_fq + (size_t)(set & 1) * n_slots_cap;
+                    q.gen_only = 0; q.qidx = set; q.fqidx = set; q.fq = e->d_k1_fq + (size_t)(set & 1) * n_slots_cap;
                     k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
                     mark(0);
                     e->launches++;
                     for (int k = 0; k < sets && set < K1S_MAX_SETS; k++, set++) {
                         K1SplitParams qf = q;
-                        qf.gen_only = 0; qf.qidx = set; qf.fq = e->d_k1_fq + (size_t)(set & 1) * n_slots_cap;
+                        qf.gen_only = 0; qf.qidx = set; qf.fqidx = set; qf.fq = e->d_k1_fq + (size_t)(set & 1) * n_slots_cap;
                         if (k + 1 < sets && set + 1 < K1S_MAX_SETS) {
                             K1SplitParams qg = q;
-                            qg.gen_only = 1; qg.qidx = set + 1;
+                            qg.gen_only = 1; qg.qidx = set + 1; qg.fqidx = set + 1;
                             k1_fused<<<e->sm_count, K1X_THREADS, sizeof(K1XSmem), stream>>>(qf, qg);
                         } else {
                             k1_filter<<<fgrid, K1F_THREADS, sizeof(K1FSmem), stream>>>(qf);
@@ -620,19 +625,28 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                     }
                     continue;
                 }
+                const int first_set = set;
                 for (int k = 0; k < sets && set < K1S_MAX_SETS; k++, set++) {
+                    // solve_batch: the sets of a round append to ONE flag queue and a single k1_solve runs after the round's
+                    // last filter (a solve over one set is a partial wave bound by the latency of one P3P)
+                    const bool batch = e->k1_solve_batch != 0;
+                    const bool solve_now = !batch || k + 1 == sets || set + 1 == K1S_MAX_SETS;
+                    const int fset = batch ? first_set : set;
                     q.gen_only = (k > 0);
                     q.qidx = set;
-                    q.fq = e->d_k1_fq + (size_t)(set & 1) * (size_t)n_slots_cap;
+                    q.fqidx = fset;
+                    q.fq = e->d_k1_fq + (size_t)(fset & 1) * (size_t)n_slots_cap;
                     k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
                     mark(0);
                     if (overlap) {
                         CU(cudaEventRecord(e->k1_ev_gen[set], stream));
                         CU(cudaStreamWaitEvent(side, e->k1_ev_gen[set], 0));
-                        if (solve_side != side && set >= 2) CU(cudaStreamWaitEvent(side, e->k1_ev_solve[set - 2], 0));   // the flag-queue region is free again
+                        if (!batch && solve_side != side && set >= 2) CU(cudaStreamWaitEvent(side, e->k1_ev_solve[set - 2], 0));   // the flag-queue region is free again
                     }
                     k1_filter<<<fgrid, K1F_THREADS, sizeof(K1FSmem), side>>>(q);
                     if (!overlap) mark(1);
+                    e->launches += 2;
+                    if (!solve_now) continue;
                     if (solve_side != side) {
                         CU(cudaEventRecord(e->k1_ev_filt[set], side));
                         CU(cudaStreamWaitEvent(solve_side, e->k1_ev_filt[set], 0));
@@ -640,7 +654,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                     k1_solve<<<e->k1_solve_grid, K1V_THREADS, 0, solve_side>>>(q);
                     if (solve_side != side) CU(cudaEventRecord(e->k1_ev_solve[set], solve_side));
                     if (!overlap) mark(2);
-                    e->launches += 3;
+                    e->launches++;
                 }
                 if (overlap) CU(cudaEventRecord(e->k1_ev_round, solve_side));
             }

@@ -184,6 +184,9 @@ DSAC_HD float approx_ex2(float x) { return exp2f(x); }
 // happen for the three points a P3P pose fits exactly) gives 0 * rsqrt(floor) = 0; A > 0 implies A >= ulp^2 and z != 0
 // implies z^2 far above the floor.  GUARDED adds cv::projectPoints' z ? 1/z : 1; *az returns |z| before that substitution
 // (the unguarded caller uses it to detect z == 0 and repeat with GUARDED).
+#ifndef DSAC_K2_FLOOR_FMA
+#define DSAC_K2_FLOOR_FMA 1   /* floor under k_score's rsqrt as an FMA addend (1) or as a separate max (0) */
+#endif
 template <bool GUARDED>
 DSAC_HD float score_pair_error(float r0x, float r0y, float r0z, float r0w, float r1x, float r1y, float r1z, float r1w, float r2x,
                                float r2y, float r2z, float r2w, float X, float Y, float Z, float pu, float pv, float* az) {
@@ -195,7 +198,13 @@ DSAC_HD float score_pair_error(float r0x, float r0y, float r0z, float r0w, float
     const float du = fmaf(pu, zs, -xs);
     const float dv = fmaf(pv, zs, -ys);
     const float A = fmaf(du, du, dv * dv);
+    // floor under the rsqrt (A = 0: a point exactly on its pixel) as the addend of an FMA instead of a separate max: for
+    // every A z^2 that is not (sub)normal-small the sum rounds to A z^2 itself, i.e. the same bits as before
+#if DSAC_K2_FLOOR_FMA
+    return fminf(A * approx_rsqrt(fmaf(A, zs * zs, 1e-30f)), DSAC_MAXINPUT_F);
+#else
     return fminf(A * approx_rsqrt(fmaxf(A * (zs * zs), 1e-30f)), DSAC_MAXINPUT_F);
+#endif
 }
 
 // Sum of the soft-inlier sigmoids sigma(beta (tau - e_j)) = 1 / (1 + 2^(kbeta e_j - tau_k)) of five errors over ONE

@@ -82,12 +82,29 @@ struct K1SplitParams {
     int round_limit;            // candidates a round may have at most (= portion * launch sets of the round)
     int qidx;                   // launch set of this call: index into wq_n / fq_n, wq region qidx * wq_stride
     int wq_stride;
+    int fqidx;                  // flag queue of this call: index into fq_n (the sets of a round may share one queue: one k1_solve per round)
     double first_frac;          // first round: this fraction of the expected need (K1S_FIRST_ROUND_FRAC; > 1 for few streams)
 };
 
 // ------------------------------------------------------------------ k1_cells
-__global__ void __launch_bounds__(256) k1_cells(K1SplitParams q, int n_frames) {
+// The trailing (n_slots + 31) / 32 blocks seed the streams instead: MT19937's seeding recurrence is serial (624 dependent
+// steps), so one THREAD per stream does it here, all streams at once and next to the cell records, instead of thread 0 of
+// every k1_slot CTA with the other 255 threads waiting (10 us per CTA, two CTA waves).
+__global__ void __launch_bounds__(256) k1_cells(K1SplitParams q, int n_frames, int cell_blocks) {
     const SampleParams& p = q.sp;
+    if ((int)blockIdx.x >= cell_blocks) {
+        const int slot = ((int)blockIdx.x - cell_blocks) * 32 + (int)threadIdx.x;
+        if (threadIdx.x >= 32 || slot >= q.n_slots) return;
+        // stream s of global frame g: mt19937(seed + g*T + s)   (thread_rand.cpp:52 for g = 0)
+        uint32_t* mt = q.state[slot].mt;
+        uint32_t v = p.seed + (uint32_t)(p.frame0 * (long long)p.T + slot);
+        mt[0] = v;
+        for (int i = 1; i < MT_N; i++) {
+            v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
+            mt[i] = v;
+        }
+        return;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_frames * DSAC_N_CONST) return;
     const int frame = i / DSAC_N_CONST, c = i - frame * DSAC_N_CONST;
@@ -189,7 +206,7 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
             return;
         }
         // stream s of global frame g: mt19937(seed + g*T + s)   (thread_rand.cpp:52 for g = 0)
-        if (tid == 0) mt_seed(sm.st, p.seed + (uint32_t)((p.frame0 + frame) * (long long)p.T + s));
+        for (int k = tid; k < MT_N; k += K1S_THREADS) sm.st[k] = S.mt[k];   // seeded by k1_cells
         pos = (s == 0) ? p.skip : 0u;
         gen = 0;
         acc = 0;
@@ -658,7 +675,7 @@ __device__ __forceinline__ void k1_filter_body(const K1SplitParams& q, K1FSmem& 
         __syncwarp();
         if (cnt > 0) {
             int at = 0;
-            if (lane == 0) at = atomicAdd(q.fq_n + q.qidx, cnt);
+            if (lane == 0) at = atomicAdd(q.fq_n + q.fqidx, cnt);
             at = __shfl_sync(0xffffffffu, at, 0);
             for (int k = lane; k < cnt; k += 32) q.fq[at + k] = ((uint32_t)slot << K1S_IDX_BITS) | (uint32_t)wl[k];
             n_flagged += (unsigned long long)cnt;
@@ -730,7 +747,7 @@ __global__ void __launch_bounds__(K1V_THREADS, K1V_MIN_BLOCKS) k1_solve(K1SplitP
     const SampleParams& p = q.sp;
     const int tid = threadIdx.x;
     constexpr int GROUP = K1V_GROUP, GROUPS = K1V_THREADS / GROUP, ROOTS = 4 / GROUP;
-    const int n_q = q.fq_n[q.qidx];
+    const int n_q = q.fq_n[q.fqidx];
     const int sub = tid % GROUP;
     for (int base = blockIdx.x * GROUPS; base < n_q; base += gridDim.x * GROUPS) {
         const int qi = base + tid / GROUP;

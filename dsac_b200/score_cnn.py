@@ -58,3 +58,22 @@ class ScoreCNN:
                 x = (dm[lo:lo + self.batch] - MEAN).to(self.dtype)        # forward(): input[...]:add(-mean)
                 sc[lo:lo + self.batch] = self.model(x).reshape(-1).double()
         return 0
+
+    def backward(self, d_diffmaps, d_score_grads, n, H, d_diffmap_grads, stream):
+        """Callable for Engine.set_score_backward_hook: the seam's adjoint `backward(maps, state, scoreOutputGradients,
+        gradients)` (`core/lua_calls.h:312-341`, Lua side `core/lua/train_score_softam.lua:93-110`): push the H clamped
+        output gradients (the engine clamps them to +-grad_clamp, `train_score_softam.lua:97`) back through the network to
+        the H x 1600 inputs.  Reads / writes the engine's DEVICE buffers in place; parameter gradients accumulate in
+        `self.model` (`.grad`) for an optimiser step by the caller, as the Lua side's `gradParams` do."""
+        ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
+        with torch.cuda.stream(ext), torch.enable_grad():
+            dm = torch.as_tensor(_DevPtr(d_diffmaps, (n * H, 1, 40, 40), "<f4"), device=self.device)
+            sg = torch.as_tensor(_DevPtr(d_score_grads, (n * H,), "<f8"), device=self.device)
+            out = torch.as_tensor(_DevPtr(d_diffmap_grads, (n * H, 1600), "<f8"), device=self.device)
+            for lo in range(0, n * H, self.batch):
+                x = (dm[lo:lo + self.batch] - MEAN).to(self.dtype).requires_grad_(True)
+                y = self.model(x).reshape(-1)
+                y.backward(sg[lo:lo + self.batch].to(self.dtype))
+                out[lo:lo + self.batch] = x.grad.reshape(-1, 1600).double()
+        return 0
+
