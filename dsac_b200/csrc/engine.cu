@@ -127,6 +127,7 @@ struct dsac_engine {
     cudaEvent_t k1_ev_round = nullptr;            // last solve of a round done
     int k1_overlap = 1;
     int k1_solve_batch = 0;                       // 1: one k1_solve per round over the flagged candidates of all its launch sets (measured SLOWER, 3.07 vs 2.92 ms per step: a per-set solve runs beside the next set's generator, a per-round one runs alone)
+    int k1_slot_threads = 0;                      // DSAC_K1_SLOT_THREADS: 256 / 512 / 1024 (0: by the number of streams)
     int k1_fused = 0;                             // 1: filter of set k and generator of set k+1 in one warp-specialised kernel (k1_fused)
     int k1_wq_stride = 0;
 };
@@ -199,7 +200,9 @@ void dsac_engine_destroy(dsac_engine* e) {
     if (e->d_phase) {
         unsigned long long h[16];
         if (cudaMemcpy(h, e->d_phase, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
-            fprintf(stderr, "[dsac K1 thread-0 cycles] A1 gen %llu  A2 bounds %llu  B filter %llu  C queue %llu  D full %llu  E advance %llu\n", h[0], h[1], h[2], h[3], h[4], h[5]);
+            fprintf(stderr, "[dsac K1 thread-0 cycles] A1 gen %llu  A2 bounds %llu  B filter %llu  C queue %llu  D full %llu  E advance %llu\n"
+                            "[dsac k1_slot thread-0 cycles] regenerate+decode %llu  scan %llu  walk %llu  starts %llu  write %llu  leftover %llu\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[11], h[12], h[13]);
         cudaFree(e->d_phase);
     }
     if (e->d_k1_dbg) {
@@ -375,6 +378,7 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         CUC(cudaEventCreateWithFlags(&e->k1_ev_round, cudaEventDisableTiming));
         if (const char* ov = getenv("DSAC_K1_OVERLAP")) e->k1_overlap = atoi(ov);
         if (const char* fu = getenv("DSAC_K1_FUSED")) e->k1_fused = atoi(fu);
+        if (const char* stt = getenv("DSAC_K1_SLOT_THREADS")) e->k1_slot_threads = atoi(stt);
         if (const char* sb = getenv("DSAC_K1_SOLVE_BATCH")) e->k1_solve_batch = atoi(sb);
         CUC(cudaFuncSetAttribute(k1_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1XSmem)));
         CUC(cudaMalloc(&e->d_k1_stats, 4 * sizeof(unsigned long long)));
@@ -572,6 +576,20 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                 e->k1_ev_kind[e->k1_ev_n] = kind;
                 cudaEventRecord(e->k1_ev[e->k1_ev_n++], stream);
             };
+            // threads per (frame, stream) of the generator.  A stream's generation is a serial chain of windows; with fewer
+            // streams than the SMs hold at 256 threads, larger CTAs shorten the parallel phases of a window (measured, step in
+            // ms at 256 / 512 / 1024 threads: 128 frames 0.931 / 0.922 / 0.934, 512 frames 1.794 / 1.811 / -; one frame
+            // 295 / - / 272 us).  The MT19937 regeneration itself (half of a window) does not scale: 227 words are independent.
+            int slot_threads = K1S_THREADS;
+            if (n_slots <= 32) slot_threads = 1024;
+            else if (n_slots <= 2 * e->sm_count) slot_threads = 512;
+            if (e->k1_slot_threads > 0) slot_threads = e->k1_slot_threads;
+            auto launch_slot = [&](const K1SplitParams& qq) {
+                const dim3 g(c.n_streams, n);
+                if (slot_threads == 1024) k1_slot_t<1024><<<g, 1024, 0, stream>>>(qq);
+                else if (slot_threads == 512) k1_slot_t<512><<<g, 512, 0, stream>>>(qq);
+                else k1_slot<<<g, K1S_THREADS, 0, stream>>>(qq);
+            };
             // with the profile on everything runs on one stream so that the event intervals are the kernels' own durations
             const bool fused = e->k1_fused != 0;
             const bool overlap = e->k1_overlap && !e->k1_profile && !fused;
@@ -605,7 +623,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                 if (fused) {
                     // one stream: slot (select + first portion), then per set { filter(k) | generator(k+1) } fused, solve(k)
                     q.gen_only = 0; q.qidx = set; q.fqidx = set; q.fq = e->d_k1_fq + (size_t)(set & 1) * n_slots_cap;
-                    k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
+                    launch_slot(q);
                     mark(0);
                     e->launches++;
                     for (int k = 0; k < sets && set < K1S_MAX_SETS; k++, set++) {
@@ -636,7 +654,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                     q.qidx = set;
                     q.fqidx = fset;
                     q.fq = e->d_k1_fq + (size_t)(fset & 1) * (size_t)n_slots_cap;
-                    k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
+                    launch_slot(q);
                     mark(0);
                     if (overlap) {
                         CU(cudaEventRecord(e->k1_ev_gen[set], stream));
@@ -660,7 +678,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             }
             if (overlap) CU(cudaStreamWaitEvent(stream, e->k1_ev_round, 0));
             q.round = n_rounds; q.select_only = 1; q.gen_only = 0;
-            k1_slot<<<dim3(c.n_streams, n), K1S_THREADS, 0, stream>>>(q);
+            launch_slot(q);
             mark(0);
             sp.resume = q.state;   // streams the rounds left unfinished (normally none) continue in the monolithic kernel
             k_sample<<<dim3(c.n_streams, n), K1_THREADS, sizeof(K1Smem), stream>>>(sp);

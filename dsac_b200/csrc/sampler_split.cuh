@@ -122,21 +122,23 @@ __global__ void __launch_bounds__(256) k1_cells(K1SplitParams q, int n_frames, i
 }
 
 // ------------------------------------------------------------------ k1_slot
-struct K1GSmem {
+template <int NW>
+struct K1GSmemT {
     uint32_t st[2 * MT_N];                       // MT19937 state, double-buffered (old / new generation)
     __align__(16) unsigned char vals[K1S_WORDS];  // Lemire value (0..39) of stream word pos+i; 255 = rejected draw
     unsigned short cand_start[K1S_SR + 512];     // word offset (from pos) where candidate i starts
     unsigned short acc_list[K1S_ACC_LIST];       // selection: accepted candidates of the round, in order
-    int warp[2][K1S_WARPS];
+    int warp[2][NW];
     uint32_t newpos;
     int n_sr, any_reject, walk_fail;
-    uint32_t ev[K1S_WARPS][K1_EV_CAP];
-    int ev_n[K1S_WARPS];
+    uint32_t ev[NW][K1_EV_CAP];
+    int ev_n[NW];
     unsigned short brk_ci[K1_BRK_CAP], brk_cur[K1_BRK_CAP];
     int brk_n;
     int sel_total;
     int or_flag;
 };
+using K1GSmem = K1GSmemT<K1S_WARPS>;
 
 // Size of the next round: enough candidates for the hypotheses still missing, from the acceptance rate observed so
 // far (cpa = candidates per accepted hypothesis) plus a margin of ~2.5 sigma of the binomial count, so that nearly
@@ -164,8 +166,10 @@ __device__ __forceinline__ int k1_round_size(int quota, int acc, long long cand_
 
 // The work of k1_slot for one (frame, stream), by a group of K1S_THREADS threads that synchronise with barrier BAR_ID
 // (0: the whole CTA of the k1_slot kernel; >= 1: the generator warps inside k1_fused).  tid: index within the group.
-template <int BAR_ID, int BAR_N>
-__device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm, const int tid, const int s, const int frame) {
+template <int BAR_ID, int BAR_N, int NT>
+__device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmemT<NT / 32>& sm, const int tid, const int s, const int frame) {
+    constexpr int NW = NT / 32, SEL_WORDS = K1S_MAX_CAP / 32 / NT;   // warps of the group; accept-bit words per thread in the selection
+    static_assert(SEL_WORDS >= 1 && K1S_LEFT_CAP % NT == 0, "k1_slot_body: thread count");
     const SampleParams& p = q.sp;
     const int lane = tid & 31, warp_id = tid >> 5;
     const int slot = frame * p.T + s;
@@ -190,9 +194,9 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
         gen = S.gen;
         {
             uint32_t* half = sm.st + ((gen / MT_N) & 1u) * MT_N;
-            for (int k = tid; k < MT_N; k += K1S_THREADS) half[k] = S.mt[k];
+            for (int k = tid; k < MT_N; k += NT) half[k] = S.mt[k];
             const int ln = S.left_n;
-            for (int k = tid; k < ln; k += K1S_THREADS) sm.vals[k] = S.left[k];
+            for (int k = tid; k < ln; k += NT) sm.vals[k] = S.left[k];
             if (tid == 0) { sm.any_reject = S.any_reject; sm.walk_fail = 0; }
         }
         group_barrier<BAR_ID, BAR_N>();
@@ -206,7 +210,7 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
             return;
         }
         // stream s of global frame g: mt19937(seed + g*T + s)   (thread_rand.cpp:52 for g = 0)
-        for (int k = tid; k < MT_N; k += K1S_THREADS) sm.st[k] = S.mt[k];   // seeded by k1_cells
+        for (int k = tid; k < MT_N; k += NT) sm.st[k] = S.mt[k];   // seeded by k1_cells
         pos = (s == 0) ? p.skip : 0u;
         gen = 0;
         acc = 0;
@@ -221,21 +225,21 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
         const int n_prev = S.n_round;
         const int n_words = (n_prev + 31) >> 5;          // <= K1S_MAX_CAP / 32
         const uint32_t* ab = q.accbits + (size_t)slot * (q.cap >> 5);
-        uint32_t w[K1S_SEL_WORDS];
+        uint32_t w[SEL_WORDS];
         int mine = 0;
 #pragma unroll
-        for (int k = 0; k < K1S_SEL_WORDS; k++) {
-            const int wi = K1S_SEL_WORDS * tid + k;
+        for (int k = 0; k < SEL_WORDS; k++) {
+            const int wi = SEL_WORDS * tid + k;
             w[k] = (wi < n_words) ? ab[wi] : 0u;
             mine += __popc(w[k]);
         }
         int tot;
-        int rank = block_excl_scan<K1S_WARPS, BAR_ID, BAR_N>(mine, &tot, sm.warp[0], tid);
+        int rank = block_excl_scan<NW, BAR_ID, BAR_N>(mine, &tot, sm.warp[0], tid);
         const int room = quota - acc;
 #pragma unroll
-        for (int k = 0; k < K1S_SEL_WORDS; k++) {
+        for (int k = 0; k < SEL_WORDS; k++) {
             uint32_t ww = w[k];
-            const int base_i = (K1S_SEL_WORDS * tid + k) * 32;
+            const int base_i = (SEL_WORDS * tid + k) * 32;
             while (ww) {
                 const int b = __ffs(ww) - 1;
                 ww &= ww - 1;
@@ -245,7 +249,7 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
         }
         group_barrier<BAR_ID, BAR_N>();
         const int n_emit = min(tot, room);
-        for (int k = tid; k < n_emit; k += K1S_THREADS) {
+        for (int k = tid; k < n_emit; k += NT) {
             const int i = sm.acc_list[k];
             const size_t hi = (size_t)frame * p.H + h0 + acc + k;
             const double* po = q.pose_out + (cbase + i) * 6;
@@ -288,9 +292,9 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
         gen = S.gen;
         {
             uint32_t* half = sm.st + ((gen / MT_N) & 1u) * MT_N;
-            for (int k = tid; k < MT_N; k += K1S_THREADS) half[k] = S.mt[k];
+            for (int k = tid; k < MT_N; k += NT) half[k] = S.mt[k];
             const int ln = S.left_n;
-            for (int k = tid; k < ln; k += K1S_THREADS) sm.vals[k] = S.left[k];
+            for (int k = tid; k < ln; k += NT) sm.vals[k] = S.left[k];
             if (tid == 0) { sm.any_reject = S.any_reject; sm.walk_fail = 0; }
         }
         group_barrier<BAR_ID, BAR_N>();
@@ -308,12 +312,21 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
     const int n_round = min(q.portion, round_total - already);   // candidates this launch generates
 
     // ---------------- generation: windows of up to K1S_SR candidates (phases A1, A2 and E of k_sample)
+    // development aid (DSAC_K1_TIMERS=1): thread-0 cycles per phase of the generator -> phase_cycles[8..13]
+    const bool timed = p.phase_cycles != nullptr && tid == 0;
+    long long t_mark = timed ? clock64() : 0, t_ph[6] = {0, 0, 0, 0, 0, 0};
+#define K1S_PHASE(k) do { if (timed) { const long long t_now = clock64(); t_ph[k] += t_now - t_mark; t_mark = t_now; } } while (0)
     int produced = 0;
     uint32_t st_par = (gen / MT_N) & 1u;   // which half of sm.st holds the current state
     while (produced < n_round) {
         const int n_target = min(K1S_SR, n_round - produced);
         const int w_need = min(K1S_WORDS - 640, n_target * 8 + 768);   // a regeneration may overshoot by 623 words
         // (leftover words [pos, gen) are at vals[0..gen-pos))
+        // One barrier per 624-word regeneration: thread t < 227 twists words t, t + 227, t + 454 (each needs the thread's own
+        // previous word and OLD neighbours only) and decodes them on the fly.  Measured alternatives (tools/micro/regen_bench.cu,
+        // a lone CTA: twist alone 382 cycles per block, twist + decode fused 504, in this kernel 677; twist and decode on
+        // separate warps 486 alone but 13 % slower with four CTAs per SM; decode of the previous block by all threads: equal):
+        // the block time is the instruction stream of the twisting warps, two per scheduler.
         while ((int)(gen - pos) < w_need) {
             const uint32_t* so = sm.st + st_par * MT_N;           // old state
             uint32_t* sn = sm.st + (st_par ^ 1u) * MT_N;            // new state
@@ -346,6 +359,7 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
             gen += MT_N;
             group_barrier<BAR_ID, BAR_N>();
         }
+        K1S_PHASE(0);   // regeneration + decode
         const int w_avail = min((int)(gen - pos), K1S_WORDS);
 
         // candidate boundaries (see k_sample, phase A2)
@@ -358,7 +372,7 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
             // instructions per pair); only blocks that contain a repeat (~1 in 60) go through the recording path.
             const uint4* v128 = reinterpret_cast<const uint4*>(sm.vals);
             const int n_blocks = (scan_end + 7) >> 3;
-            const int bseg = ((n_blocks + K1S_WARPS - 1) / K1S_WARPS + 31) & ~31;   // blocks per warp, contiguous: events stay ordered
+            const int bseg = ((n_blocks + NW - 1) / NW + 31) & ~31;   // blocks per warp, contiguous: events stay ordered
             const int bbeg = warp_id * bseg, bend = min(bbeg + bseg, n_blocks);
             int cnt = 0;
             for (int b0 = bbeg; b0 < bend; b0 += 32) {
@@ -411,11 +425,12 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
             }
             if (lane == 0) sm.ev_n[warp_id] = cnt;
             group_barrier<BAR_ID, BAR_N>();
+            K1S_PHASE(1);   // scan for repeated pairs
             if (tid == 0) {
                 int cur = 0, ci = 0, nb = 1, stop_at = -1;
                 bool fail = false;
                 sm.brk_ci[0] = 0; sm.brk_cur[0] = 0;
-                for (int w = 0; w < K1S_WARPS && !fail && stop_at < 0; w++) {
+                for (int w = 0; w < NW && !fail && stop_at < 0; w++) {
                     const int n = sm.ev_n[w];
                     if (n > K1_EV_CAP) { fail = true; break; }
                     for (int e = 0; e < n; e++) {
@@ -442,10 +457,11 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
                 sm.walk_fail = fail ? 1 : 0;
             }
             group_barrier<BAR_ID, BAR_N>();
+            K1S_PHASE(2);   // thread 0's walk over the events
             if (!sm.walk_fail) {
                 const int n_ok = sm.n_sr, nb = sm.brk_n;
                 int m = 0;
-                for (int i = tid; i <= n_ok; i += K1S_THREADS) {
+                for (int i = tid; i <= n_ok; i += NT) {
                     while (m + 1 < nb && (int)sm.brk_ci[m + 1] <= i) m++;
                     sm.cand_start[i] = (unsigned short)(2 * ((int)sm.brk_cur[m] + 4 * (i - (int)sm.brk_ci[m])));
                 }
@@ -456,11 +472,11 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
             int rp = 0, n_done = 0, par = 0;   // word offset of the chunk, candidates placed so far
             bool out_of_words = false;
             while (n_done < n_target && !out_of_words) {
-                const int n_chunk = min(K1S_THREADS, n_target - n_done);
+                const int n_chunk = min(NT, n_target - n_done);
                 int extra = 0, start = 0, qn = 0;
                 for (;;) {
                     int tot;
-                    const int excl = block_excl_scan<K1S_WARPS, BAR_ID, BAR_N>(extra, &tot, sm.warp[par], tid);
+                    const int excl = block_excl_scan<NW, BAR_ID, BAR_N>(extra, &tot, sm.warp[par], tid);
                     par ^= 1;
                     start = rp + 8 * tid + excl;
                     int cells[4];
@@ -470,14 +486,14 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
                     extra = ne;
                     if (!group_barrier_or<BAR_ID, BAR_N>(changed, &sm.or_flag, tid)) break;
                 }
-                int bad = (tid < n_chunk && qn < 0) ? tid : K1S_THREADS;
+                int bad = (tid < n_chunk && qn < 0) ? tid : NT;
 #pragma unroll
                 for (int off = 16; off; off >>= 1) bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, off));
                 if (lane == 0) sm.warp[par][tid >> 5] = bad;
                 group_barrier<BAR_ID, BAR_N>();
                 int n_ok = n_chunk;
 #pragma unroll
-                for (int w = 0; w < K1S_WARPS; w++) n_ok = min(n_ok, sm.warp[par][w]);
+                for (int w = 0; w < NW; w++) n_ok = min(n_ok, sm.warp[par][w]);
                 par ^= 1;
                 if (tid < n_ok) sm.cand_start[n_done + tid] = (unsigned short)start;
                 if (tid == n_ok - 1) sm.newpos = (uint32_t)qn;          // end of the last complete candidate
@@ -492,32 +508,34 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
             }
         }
         group_barrier<BAR_ID, BAR_N>();
+        K1S_PHASE(3);   // candidate start offsets
         const int n_sr = sm.n_sr;
 
         // the window's candidates to HBM
-        for (int i = tid; i < n_sr; i += K1S_THREADS) {
+        for (int i = tid; i < n_sr; i += NT) {
             int cells[4];
             cand_parse_fast(sm.vals, sm.cand_start[i], w_avail, cells);
             q.cells[cbase + already + produced + i] = make_uint2((uint32_t)cells[0] | ((uint32_t)cells[1] << 16), (uint32_t)cells[2] | ((uint32_t)cells[3] << 16));
             q.endw[cbase + already + produced + i] = pos + (uint32_t)sm.cand_start[i + 1];
         }
 
+        K1S_PHASE(4);   // candidates to HBM (thread 0's share)
         // advance the stream: the unread tail of the window moves to the front
         {
             const int consumed = sm.cand_start[n_sr];
             const int left = w_avail - consumed;
-            unsigned char keep[K1S_LEFT_CAP / K1S_THREADS];
+            unsigned char keep[K1S_LEFT_CAP / NT];
             group_barrier<BAR_ID, BAR_N>();
 #pragma unroll
-            for (int k = 0; k < K1S_LEFT_CAP / K1S_THREADS; k++) {
-                const int i = tid + k * K1S_THREADS;
+            for (int k = 0; k < K1S_LEFT_CAP / NT; k++) {
+                const int i = tid + k * NT;
                 keep[k] = (i < left) ? sm.vals[consumed + i] : (unsigned char)0;
             }
             group_barrier<BAR_ID, BAR_N>();
             bool rej_left = false;
 #pragma unroll
-            for (int k = 0; k < K1S_LEFT_CAP / K1S_THREADS; k++) {
-                const int i = tid + k * K1S_THREADS;
+            for (int k = 0; k < K1S_LEFT_CAP / NT; k++) {
+                const int i = tid + k * NT;
                 if (i < left) {
                     sm.vals[i] = keep[k];
                     rej_left |= (keep[k] == 255);
@@ -531,17 +549,21 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
             produced += n_sr;
             group_barrier<BAR_ID, BAR_N>();
         }
+        K1S_PHASE(5);   // leftover move
         if (n_sr == 0) break;   // (cannot happen: every window holds at least one candidate)
     }
+    if (timed)
+        for (int k = 0; k < 6; k++) atomicAdd(p.phase_cycles + 8 + k, (unsigned long long)t_ph[k]);
+#undef K1S_PHASE
 
     // ---------------- hand the portion over: state, work items, cleared accept bits
     {
         const int left = min((int)(gen - pos), K1S_LEFT_CAP);
         const uint32_t* half = sm.st + ((gen / MT_N) & 1u) * MT_N;
-        for (int k = tid; k < MT_N; k += K1S_THREADS) S.mt[k] = half[k];
-        for (int k = tid; k < left; k += K1S_THREADS) S.left[k] = sm.vals[k];
+        for (int k = tid; k < MT_N; k += NT) S.mt[k] = half[k];
+        for (int k = tid; k < left; k += NT) S.left[k] = sm.vals[k];
         uint32_t* ab = q.accbits + (size_t)slot * (q.cap >> 5) + (already >> 5);   // `already` is a multiple of the chunk size
-        for (int k = tid; k < ((produced + 31) >> 5); k += K1S_THREADS) ab[k] = 0u;
+        for (int k = tid; k < ((produced + 31) >> 5); k += NT) ab[k] = 0u;
         if (tid == 0) {
             S.pos = pos; S.gen = gen; S.acc = acc; S.cand_base = cand_base; S.n_round = already + produced; S.done = 0;
             if (!q.gen_only) S.target = round_total;
@@ -566,9 +588,17 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmem& sm
 #ifndef K1S_MIN_BLOCKS
 #define K1S_MIN_BLOCKS 4
 #endif
+// NT threads per (frame, stream): 256 (4 CTAs per SM) when there are streams to fill the GPU several times over; 512 or
+// 1024 when there are fewer streams than SMs can hold -- a stream's generation is a serial chain of windows, and the time of
+// a lone CTA is what a small batch (single-frame latency, strong scaling) waits for.
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT == K1S_THREADS) ? K1S_MIN_BLOCKS : 1024 / NT) k1_slot_t(K1SplitParams q) {
+    __shared__ K1GSmemT<NT / 32> sm;
+    k1_slot_body<0, 0, NT>(q, sm, threadIdx.x, blockIdx.x, blockIdx.y);
+}
 __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitParams q) {
     __shared__ K1GSmem sm;
-    k1_slot_body<0, 0>(q, sm, threadIdx.x, blockIdx.x, blockIdx.y);
+    k1_slot_body<0, 0, K1S_THREADS>(q, sm, threadIdx.x, blockIdx.x, blockIdx.y);
 }
 
 // ------------------------------------------------------------------ k1_filter
@@ -731,7 +761,7 @@ __global__ void __launch_bounds__(K1X_THREADS, 1) k1_fused(K1SplitParams qf, K1S
         const int tid = threadIdx.x - K1X_FILTER_THREADS;
         const int T = qg.sp.T;
         for (int slot = blockIdx.x; slot < qg.n_slots; slot += gridDim.x) {
-            k1_slot_body<1, K1X_GEN_THREADS>(qg, sm.g, tid, slot % T, slot / T);
+            k1_slot_body<1, K1X_GEN_THREADS, K1X_GEN_THREADS>(qg, sm.g, tid, slot % T, slot / T);
             group_barrier<1, K1X_GEN_THREADS>();   // the group's shared memory is reused by the next slot
         }
     }
