@@ -599,7 +599,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             mark(-1);
             {
                 const int cell_blocks = (int)(((size_t)n * Nn + 255) / 256), seed_blocks = (int)((n_slots + 31) / 32);
-                k1_cells<<<(unsigned)(cell_blocks + seed_blocks), 256, 0, stream>>>(q, n, cell_blocks);
+                k1_cells<<<(unsigned)(cell_blocks + seed_blocks), 256, 0, stream>>>(q, n, seed_blocks);
             }
             mark(0);
             e->launches++;

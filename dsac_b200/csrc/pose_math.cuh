@@ -811,8 +811,9 @@ DSAC_HD bool p3p_quick_core(const double bear[3][3], const double X[4][3], doubl
     const double e2x = e3y * e1z - e3z * e1y, e2y = e3z * e1x - e3x * e1z, e2z = e3x * e1y - e3y * e1x;
     const double wx = X[3][0] - X[0][0], wy = X[3][1] - X[0][1], wz = X[3][2] - X[0][2];
     const double al = wx * e1x + wy * e1y + wz * e1z, be = wx * e2x + wy * e2y + wz * e2z, ga = wx * e3x + wy * e3y + wz * e3z;
+#if !DSAC_FILTER_FP32_TAIL
     const double lim2 = (thr + DSAC_FILTER_BAND_PX) * (thr + DSAC_FILTER_BAND_PX);
-#if DSAC_FILTER_FP32_TAIL
+#else
     const float b0x = (float)bear[0][0], b0y = (float)bear[0][1], b0z = (float)bear[0][2];
     const float b1x = (float)bear[1][0], b1y = (float)bear[1][1], b1z = (float)bear[1][2];
     const float b2x = (float)bear[2][0], b2y = (float)bear[2][1], b2z = (float)bear[2][2];

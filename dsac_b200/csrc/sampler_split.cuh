@@ -87,25 +87,33 @@ struct K1SplitParams {
 };
 
 // ------------------------------------------------------------------ k1_cells
-// The trailing (n_slots + 31) / 32 blocks seed the streams instead: MT19937's seeding recurrence is serial (624 dependent
+// The FIRST (n_slots + 31) / 32 blocks seed the streams instead: MT19937's seeding recurrence is serial (624 dependent
 // steps), so one THREAD per stream does it here, all streams at once and next to the cell records, instead of thread 0 of
-// every k1_slot CTA with the other 255 threads waiting (10 us per CTA, two CTA waves).
-__global__ void __launch_bounds__(256) k1_cells(K1SplitParams q, int n_frames, int cell_blocks) {
+// every k1_slot CTA with the other 255 threads waiting (10 us per CTA, two CTA waves).  A warp seeds 32 streams in lockstep
+// and hands every 32 steps over through a shared-memory tile, so that the states reach HBM as 128-byte rows.
+__global__ void __launch_bounds__(256) k1_cells(K1SplitParams q, int n_frames, int seed_blocks) {
     const SampleParams& p = q.sp;
-    if ((int)blockIdx.x >= cell_blocks) {
-        const int slot = ((int)blockIdx.x - cell_blocks) * 32 + (int)threadIdx.x;
-        if (threadIdx.x >= 32 || slot >= q.n_slots) return;
+    __shared__ uint32_t tile[32][33];
+    if ((int)blockIdx.x < seed_blocks) {
+        if (threadIdx.x >= 32) return;
+        const int lane = (int)threadIdx.x, slot0 = (int)blockIdx.x * 32, slot = slot0 + lane;
         // stream s of global frame g: mt19937(seed + g*T + s)   (thread_rand.cpp:52 for g = 0)
-        uint32_t* mt = q.state[slot].mt;
         uint32_t v = p.seed + (uint32_t)(p.frame0 * (long long)p.T + slot);
-        mt[0] = v;
-        for (int i = 1; i < MT_N; i++) {
-            v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
-            mt[i] = v;
+        for (int i0 = 0; i0 < MT_N; i0 += 32) {
+#pragma unroll 8
+            for (int j = 0; j < 32; j++) {
+                const int i = i0 + j;
+                if (i > 0) v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
+                tile[lane][j] = v;
+            }
+            __syncwarp();
+            if (i0 + lane < MT_N)
+                for (int r = 0; r < 32 && slot0 + r < q.n_slots; r++) q.state[slot0 + r].mt[i0 + lane] = tile[r][lane];
+            __syncwarp();
         }
         return;
     }
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = ((int)blockIdx.x - seed_blocks) * blockDim.x + threadIdx.x;
     if (i >= n_frames * DSAC_N_CONST) return;
     const int frame = i / DSAC_N_CONST, c = i - frame * DSAC_N_CONST;
     const int16_t* coords = p.coords + (size_t)frame * DSAC_N_CONST * 3;
@@ -372,8 +380,11 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmemT<NT
             // instructions per pair); only blocks that contain a repeat (~1 in 60) go through the recording path.
             const uint4* v128 = reinterpret_cast<const uint4*>(sm.vals);
             const int n_blocks = (scan_end + 7) >> 3;
-            const int bseg = ((n_blocks + NW - 1) / NW + 31) & ~31;   // blocks per warp, contiguous: events stay ordered
-            const int bbeg = warp_id * bseg, bend = min(bbeg + bseg, n_blocks);
+            // (at most 8 warps scan: the walking thread below visits one event list per scanning warp, and with 32 lists the
+            // serial walk cost more than the scan gained -- thread-0 cycles per frame 112 k vs 77 k)
+            constexpr int NWS = NW < 8 ? NW : 8;
+            const int bseg = ((n_blocks + NWS - 1) / NWS + 31) & ~31;   // blocks per warp, contiguous: events stay ordered
+            const int bbeg = min(warp_id * bseg, n_blocks), bend = (warp_id < NWS) ? min(bbeg + bseg, n_blocks) : bbeg;
             int cnt = 0;
             for (int b0 = bbeg; b0 < bend; b0 += 32) {
                 const int b = b0 + lane;
@@ -423,14 +434,14 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmemT<NT
                     cnt += tot;
                 }
             }
-            if (lane == 0) sm.ev_n[warp_id] = cnt;
+            if (lane == 0 && warp_id < NWS) sm.ev_n[warp_id] = cnt;
             group_barrier<BAR_ID, BAR_N>();
             K1S_PHASE(1);   // scan for repeated pairs
             if (tid == 0) {
                 int cur = 0, ci = 0, nb = 1, stop_at = -1;
                 bool fail = false;
                 sm.brk_ci[0] = 0; sm.brk_cur[0] = 0;
-                for (int w = 0; w < NW && !fail && stop_at < 0; w++) {
+                for (int w = 0; w < NWS && !fail && stop_at < 0; w++) {
                     const int n = sm.ev_n[w];
                     if (n > K1_EV_CAP) { fail = true; break; }
                     for (int e = 0; e < n; e++) {
