@@ -385,6 +385,11 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    filt_traffic = None
+    try:
+        filt_traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_filter_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        filt_traffic = None
     ssum = sum(stage_ms.values())
     kernels_ms = {"k1_cells+k1_slot (MT19937 streams, candidate boundaries, ordered selection)": k1_ms[0],
                   "k1_filter (conservative fp64 P3P filter, 1 thread per candidate)": k1_ms[1],
@@ -397,9 +402,11 @@ def main():
     flops_alg = (FILTER_FLOPS_SETUP + FILTER_MEAN_ROOTS * FILTER_FLOPS_ROOT) * k1_cnt[0]
     flops_exec = (FILTER_FLOPS_SETUP + FILTER_EXEC_SLOTS * FILTER_FLOPS_ROOT) * k1_cnt[0]
     roofline = {"kernel": "k1_filter (dominant: %.0f %% of the stage-isolated step) -- conservative fp64 P3P filter over every sampled minimal set" % (100 * k1_ms[1] / ssum),
-                "bound": "fp64 pipe (not hbm / tensor: point-wise fp64 arithmetic on data staged in shared memory; see roofline_hbm for the HBM-bound kernel)",
+                "bound": "fp64",
+                "bound_note": "fp64 pipe, not hbm / tensor: point-wise fp64 arithmetic on data staged in shared memory (DRAM throughput 4 % of peak under ncu); see roofline_hbm for the HBM-bound kernel of the path",
                 "achieved": flops_alg / filt_s / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": flops_alg / filt_s / 1e12 / FP64_PEAK_TFLOPS,
-                "traffic": None, "peak_source": "148 SMs x 64 fp64 FMA/clk x 2 x 1.965 GHz (no measured fp64 peak in MEASURED_PEAKS.json)",
+                "traffic": filt_traffic, "traffic_note": "DRAM bytes of ONE k1_filter launch (launch set 0: 4 194 304 candidates) from the committed ncu --set full capture, profiles/k1_filter_traffic.json",
+                "peak_source": "148 SMs x 64 fp64 FMA/clk x 2 x 1.965 GHz (no measured fp64 peak in MEASURED_PEAKS.json)",
                 "algorithmic_flops_per_candidate": FILTER_FLOPS_SETUP + FILTER_MEAN_ROOTS * FILTER_FLOPS_ROOT,
                 "fp32_flops_per_candidate_beside": FILTER_MEAN_ROOTS * FILTER_FP32_ROOT,
                 "executed_flops_per_candidate": FILTER_FLOPS_SETUP + FILTER_EXEC_SLOTS * FILTER_FLOPS_ROOT, "executed_frac": flops_exec / filt_s / 1e12 / FP64_PEAK_TFLOPS,
