@@ -60,6 +60,23 @@ def test_forward_matches_oracle(engine_mod, oracle, T, H):
     eng.close()
 
 
+@pytest.mark.parametrize("threads", [256, 512, 1024])
+def test_generator_thread_counts_sample_the_same_sets(engine_mod, oracle, threads, monkeypatch):
+    """k1_slot is instantiated for 256 / 512 / 1024 threads per (frame, stream) and chosen by the number of streams
+    (engine.cu); every instantiation must give the oracle's minimal sets, candidate for candidate."""
+    E, O = engine_mod, oracle
+    nf, T, H = 5, 3, 64
+    monkeypatch.setenv("DSAC_K1_SLOT_THREADS", str(threads))
+    coords, pix, gt_cv, gt_jp = E.synth_frames(nf, n_streams=T)
+    eng = E.Engine(max_frames=nf, n_streams=T, n_hyps=H)
+    res = eng.forward(coords, pix, gt_jp)
+    eng.close()
+    for f in range(nf):
+        fw = _oracle_frame(O, dict(n_hyps=H), coords[f], pix[f], gt_jp[f], f, T)
+        assert np.array_equal(fw.img_idx, res.img_idx[f]) and np.array_equal(fw.cand_idx, res.cand_idx[f])
+        assert fw.n_candidates == res.n_candidates[f] and res.status[f] == 0
+
+
 def test_refine_is_exact_given_the_same_start(engine_mod, oracle):
     """K4 alone (fp64): start the oracle's refine() from the GPU's own average pose."""
     E, O = engine_mod, oracle
