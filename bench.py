@@ -231,8 +231,20 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not mix with the ONE JSON line on stdout
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's debug lines must not mix with the ONE JSON line on stdout
+        # ... and its "NCCL version" banner is printed to stdout regardless (seen on the 2-GPU box): file descriptor 1 points
+        # at stderr while the communicator is set up (init + the first collective)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if world > 1:
