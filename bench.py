@@ -457,28 +457,52 @@ def main():
 
     # ---- config 2: single frame latency (1 frame, 256 hyp, forward scoring + soft-argmax)
     single = None
+    config1 = None
     if rank == 0:
-        single = {"workload": "config 2: 1 frame x 256 hyp x 1600 pts, sample+score+soft-argmax (CUDA events, 200 reps)"}
+        def frame_latency(H1, T, stages, reps=1000, warm=100):
+            """One frame per call; every call bracketed by its own pair of CUDA events on the launching stream; median."""
+            d1 = E.synth_frames(1, frame0=frame0, n_streams=T)
+            c1 = torch.from_numpy(d1[0]).cuda(); p1 = torch.from_numpy(d1[1]).cuda(); g1 = torch.from_numpy(d1[3]).cuda()
+            eng1 = E.Engine(max_frames=1, device=local_rank, n_streams=T, n_hyps=H1)
+            eng1.set_stages(stages)
+            for _ in range(warm):
+                eng1.forward_device(1, c1.data_ptr(), p1.data_ptr(), 0, g1.data_ptr(), frame0, stream)
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for a, b in ev:
+                a.record()
+                eng1.forward_device(1, c1.data_ptr(), p1.data_ptr(), 0, g1.data_ptr(), frame0, stream)
+                b.record()
+            torch.cuda.synchronize()
+            us = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+            eng1.close()
+            return us[len(us) // 2], us[len(us) // 10], us[(9 * len(us)) // 10]
+
+        single = {"workload": "config 2: 1 frame x 256 hyp x 1600 pts, sample+score+soft-argmax (a CUDA-event pair per call, median of 1000 after 100 warm-ups)"}
         # n_streams is part of the sampler contract (= OpenMP threads of the reference loop): 1 reproduces
         # OMP_NUM_THREADS=1, 8 an 8-thread run; more streams = more CTAs sampling the one frame in parallel
         for T in (1, 8):
-            d1 = E.synth_frames(1, frame0=frame0, n_streams=T)
-            c1 = torch.from_numpy(d1[0]).cuda(); p1 = torch.from_numpy(d1[1]).cuda(); g1 = torch.from_numpy(d1[3]).cuda()
-            eng1 = E.Engine(max_frames=1, device=local_rank, n_streams=T)
-            eng1.set_stages(E.STAGE_SAMPLE | E.STAGE_SCORE)
-            for _ in range(20):
-                eng1.forward_device(1, c1.data_ptr(), p1.data_ptr(), 0, g1.data_ptr(), frame0, stream)
-            torch.cuda.synchronize()
-            reps = 200
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                eng1.forward_device(1, c1.data_ptr(), p1.data_ptr(), 0, g1.data_ptr(), frame0, stream)
-            e1.record()
-            e1.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / reps
-            single["streams_%d" % T] = {"latency_us": us, "hyp_per_s": H / (us * 1e-6)}
-            eng1.close()
+            med, p10, p90 = frame_latency(H, T, E.STAGE_SAMPLE | E.STAGE_SCORE)
+            single["streams_%d" % T] = {"latency_us": med, "p10_us": p10, "p90_us": p90, "hyp_per_s": H / (med * 1e-6)}
+        single["bound"] = "latency: one stream is one generator CTA -- 282 serial MT19937 state regenerations + 11 windows of scan / walk / write (DESIGN.md section 9)"
+        # config 1: the reference's own CPU-runnable case (1 frame, 64 hypotheses, full test pipeline)
+        med1, p10_1, p90_1 = frame_latency(64, 1, E.STAGE_ALL)
+        config1 = {"workload": "config 1: 1 frame x 64 hyp x 1600 pts, full test pipeline (sample+score+softargmax+refine+eval)",
+                   "gpu_latency_us": med1, "gpu_hyp_per_s": 64 / (med1 * 1e-6)}
+        if world == 1:
+            try:
+                from dsac_b200 import synth
+                from oracle import oracle as O
+                variant, flags = pick_cpu_variant()
+                cs, ps, _, _ = synth.synth_frames(16, frame0=frame0)
+                cfg1 = O.default_config(seed=1305 + frame0, n_hyps=64)
+                O.bench_forward(cfg1, cs[:2], ps[:2], n_threads=1, with_refine=True, variant=variant)
+                secs = O.bench_forward(cfg1, cs, ps, n_threads=1, with_refine=True, variant=variant)
+                config1["cpu_ms_per_frame_1thread"] = secs * 1e3 / 16
+                config1["cpu_hyp_per_s_1thread"] = 16 * 64 / secs
+                config1["cpu_build"] = flags
+            except Exception as ex:   # the CPU leg is informational
+                config1["cpu_error"] = str(ex)[:200]
 
     # ---- config 3: 256 hyp, 8 refinement iterations + soft-argmax backward (one training round per frame)
     train = None
@@ -623,6 +647,7 @@ def main():
             "sequence": sequence,
             "cpu_baseline": cpu,
             "single_frame": single,
+            "config1": config1,
             "train_round": train,
             "upstream": upstream,
             "quality": quality,

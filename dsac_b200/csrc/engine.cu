@@ -126,6 +126,7 @@ struct dsac_engine {
     cudaEvent_t k1_ev_gen[K1S_MAX_SETS] = {};     // generation of launch set i done
     cudaEvent_t k1_ev_round = nullptr;            // last solve of a round done
     int k1_overlap = 1;
+    bool k1_overlap_fixed = false;                // DSAC_K1_OVERLAP given
     int k1_solve_batch = 0;                       // 1: one k1_solve per round over the flagged candidates of all its launch sets (measured SLOWER, 3.07 vs 2.92 ms per step: a per-set solve runs beside the next set's generator, a per-round one runs alone)
     int k1_slot_threads = 0;                      // DSAC_K1_SLOT_THREADS: 256 / 512 / 1024 (0: by the number of streams)
     int k1_fused = 0;                             // 1: filter of set k and generator of set k+1 in one warp-specialised kernel (k1_fused)
@@ -376,7 +377,7 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         }
         for (int i = 0; i < K1S_MAX_SETS; i++) CUC(cudaEventCreateWithFlags(&e->k1_ev_gen[i], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&e->k1_ev_round, cudaEventDisableTiming));
-        if (const char* ov = getenv("DSAC_K1_OVERLAP")) e->k1_overlap = atoi(ov);
+        if (const char* ov = getenv("DSAC_K1_OVERLAP")) { e->k1_overlap = atoi(ov); e->k1_overlap_fixed = true; }
         if (const char* fu = getenv("DSAC_K1_FUSED")) e->k1_fused = atoi(fu);
         if (const char* stt = getenv("DSAC_K1_SLOT_THREADS")) e->k1_slot_threads = atoi(stt);
         if (const char* sb = getenv("DSAC_K1_SOLVE_BATCH")) e->k1_solve_batch = atoi(sb);
@@ -553,7 +554,14 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             const long long n_slots = (long long)n * c.n_streams;
             // a round is generated in up to 4 portions of cap / 4 candidates (round 0: 4, round 1: 2, later rounds: the whole
             // round at once); a filter work item is a chunk of a portion
-            const int portion4 = e->k1_cap / 4;
+            int n_port = 4;                       // portions of round 0 (round 1: half as many, twice as large)
+            bool port_forced = false;
+            if (const char* pp = getenv("DSAC_K1_PORTIONS")) {
+                const int v = atoi(pp);
+                if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) { n_port = v; port_forced = true; }
+            }
+            if (!port_forced && n_slots < 256) n_port = 2;   // measured at 128 frames: 2 / 4 / 8 / 16 portions 0.885 / 0.896 / 0.951 / 1.207 ms per step (1024 frames: 2.94 / 2.89 / 2.97 / -)
+            const int portion4 = e->k1_cap / n_port;
             int want_chunk = n_slots >= 512 ? 2048 : (n_slots >= 64 ? 512 : 256);
             if (const char* ch = getenv("DSAC_K1_CHUNK")) want_chunk = std::max(256, atoi(ch));
             q.chunk = 256;
@@ -592,9 +600,14 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             };
             // with the profile on everything runs on one stream so that the event intervals are the kernels' own durations
             const bool fused = e->k1_fused != 0;
-            const bool overlap = e->k1_overlap && !e->k1_profile && !fused;
+            // streams: generator on `stream`, filter (and solve) on a side stream; with a batch that does not fill the GPU several
+            // times over the solve gets a stream of its own, so that the filter of set k+1 need not wait for the solve of set k
+            // (measured, ms per step with the solve on the filter's stream / on its own: 128 frames 0.938 / 0.896, 256 frames
+            // 1.21 / 1.18, 512 frames 1.78 / 1.69, 1024 frames 2.92 / 2.96)
+            const int ov_mode = e->k1_overlap_fixed ? e->k1_overlap : (n_slots <= 768 ? 2 : 1);
+            const bool overlap = ov_mode && !e->k1_profile && !fused;
             cudaStream_t side = overlap ? e->k1_side : stream;
-            cudaStream_t solve_side = (overlap && e->k1_overlap >= 2) ? e->k1_side2 : side;
+            cudaStream_t solve_side = (overlap && ov_mode >= 2) ? e->k1_side2 : side;
             const size_t n_slots_cap = (size_t)e->cfg.max_frames * c.n_streams * (size_t)e->k1_cap;
             mark(-1);
             {
@@ -613,8 +626,8 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             for (int r = 0; r < n_rounds; r++) {
                 // portions only pay when the generator has the whole GPU to fill (many streams); a few streams (single-frame
                 // latency, BASELINE config 2) take every round in one launch set: fewer dependent launches
-                const bool portioned = n_slots >= 128 && r < 2;
-                const int sets = portioned ? (r == 0 ? 4 : 2) : 1;
+                const bool portioned = (n_slots >= 128 || port_forced) && r < 2 && n_port > 1;
+                const int sets = portioned ? (r == 0 ? n_port : n_port / 2) : 1;
                 q.round = r;
                 q.portion = portioned ? (r == 0 ? portion4 : 2 * portion4) : e->k1_cap;   // round 1 may use the whole capacity too
                 q.round_limit = q.portion * sets;
