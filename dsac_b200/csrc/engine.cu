@@ -128,6 +128,13 @@ struct dsac_engine {
     int k1_overlap = 1;
     bool k1_overlap_fixed = false;                // DSAC_K1_OVERLAP given
     int k1_solve_batch = 0;                       // 1: one k1_solve per round over the flagged candidates of all its launch sets (measured SLOWER, 3.07 vs 2.92 ms per step: a per-set solve runs beside the next set's generator, a per-round one runs alone)
+    K1SlotState* d_k1_vstate = nullptr;           // k1_spec: virtual slots of the speculative first round (few streams)
+    uint2* d_k1_vcells = nullptr;
+    uint32_t* d_k1_vendw = nullptr;
+    int* d_k1_spec_result = nullptr;
+    int* d_k1_spec_table = nullptr;
+    int k1_spec_slots = 0;                        // streams the scratch above was sized for (0: speculative round off)
+    int k1_solve_group4 = 1;                      // DSAC_K1_SOLVE4: four lanes per flagged candidate for a few streams
     int k1_slot_threads = 0;                      // DSAC_K1_SLOT_THREADS: 256 / 512 / 1024 (0: by the number of streams)
     int k1_fused = 0;                             // 1: filter of set k and generator of set k+1 in one warp-specialised kernel (k1_fused)
     int k1_wq_stride = 0;
@@ -206,6 +213,12 @@ void dsac_engine_destroy(dsac_engine* e) {
                     h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[11], h[12], h[13]);
         cudaFree(e->d_phase);
     }
+    if (e->d_k1_dbg && e->d_k1_spec_result && e->k1_spec_slots > 0) {
+        int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cudaMemcpy(h, e->d_k1_spec_result, std::min(8, e->k1_spec_slots) * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess)
+            fprintf(stderr, "[dsac k1_spec, last call] windows stitched per stream (0 = speculation abandoned or not used): %d %d %d %d %d %d %d %d\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+    }
     if (e->d_k1_dbg) {
         unsigned long long h[K1S_MAX_ROUNDS * 4];
         if (cudaMemcpy(h, e->d_k1_dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -220,7 +233,7 @@ void dsac_engine_destroy(dsac_engine* e) {
     for (cudaEvent_t ev : e->k1_ev_solve) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->k1_ev_gen) if (ev) cudaEventDestroy(ev);
     if (e->k1_ev_round) cudaEventDestroy(e->k1_ev_round);
-    void* k1ptrs[] = {e->d_k1_state, e->d_k1_celltab, e->d_k1_cells, e->d_k1_endw, e->d_k1_accbits, e->d_k1_pose, e->d_k1_wq,
+    void* k1ptrs[] = {e->d_k1_spec_table, e->d_k1_vstate, e->d_k1_vcells, e->d_k1_vendw, e->d_k1_spec_result, e->d_k1_state, e->d_k1_celltab, e->d_k1_cells, e->d_k1_endw, e->d_k1_accbits, e->d_k1_pose, e->d_k1_wq,
                       e->d_k1_fq, e->d_k1_counters, e->d_k1_stats, e->d_k1_dbg};
     for (void* p : k1ptrs)
         if (p) cudaFree(p);
@@ -362,6 +375,20 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         CUC(cudaMalloc(&e->d_k1_wq, (size_t)K1S_MAX_SETS * slots * 128 * sizeof(uint2)));
         CUC(cudaMalloc(&e->d_k1_fq, 2 * slots * cap * sizeof(uint32_t)));   // two regions: the filter of set k+1 writes one while the solve of set k reads the other
         CUC(cudaMalloc(&e->d_k1_counters, 2 * K1S_MAX_SETS * sizeof(int)));
+        {   // speculative first round for a few streams (sampler_split.cuh: k1_spec / k1_stitch); DSAC_K1_SPEC=0 turns it off
+            int want = 1;
+            if (const char* sv = getenv("DSAC_K1_SPEC")) want = atoi(sv);
+            if (want) {
+                const size_t ss = std::min<size_t>(slots, 8);
+                CUC(cudaMalloc(&e->d_k1_vstate, ss * K1P_VPER * sizeof(K1SlotState)));
+                CUC(cudaMalloc(&e->d_k1_vcells, ss * K1P_VPER * K1P_CAPW * sizeof(uint2)));
+                CUC(cudaMalloc(&e->d_k1_vendw, ss * K1P_VPER * K1P_CAPW * sizeof(uint32_t)));
+                CUC(cudaMalloc(&e->d_k1_spec_result, ss * sizeof(int)));
+                CUC(cudaMemset(e->d_k1_spec_result, 0, ss * sizeof(int)));
+                CUC(cudaMalloc(&e->d_k1_spec_table, ss * K1P_TABLE * sizeof(int)));
+                e->k1_spec_slots = (int)ss;
+            }
+        }
         {   // the fp64 kernels get the higher priority: when a generator launch and a filter launch become ready together,
             // the persistent filter CTAs are placed first and the generator's CTAs fill the registers they leave free
             int least = 0, greatest = 0;
@@ -380,6 +407,7 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         if (const char* ov = getenv("DSAC_K1_OVERLAP")) { e->k1_overlap = atoi(ov); e->k1_overlap_fixed = true; }
         if (const char* fu = getenv("DSAC_K1_FUSED")) e->k1_fused = atoi(fu);
         if (const char* stt = getenv("DSAC_K1_SLOT_THREADS")) e->k1_slot_threads = atoi(stt);
+        if (const char* s4 = getenv("DSAC_K1_SOLVE4")) e->k1_solve_group4 = atoi(s4);
         if (const char* sb = getenv("DSAC_K1_SOLVE_BATCH")) e->k1_solve_batch = atoi(sb);
         CUC(cudaFuncSetAttribute(k1_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1XSmem)));
         CUC(cudaMalloc(&e->d_k1_stats, 4 * sizeof(unsigned long long)));
@@ -546,6 +574,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             q.wq_n = e->d_k1_counters; q.fq_n = e->d_k1_counters + K1S_MAX_SETS;
             q.wq_stride = e->k1_wq_stride;
             q.first_frac = (double)K1S_FIRST_ROUND_FRAC;
+            q.spec = 0;
             const int par = (int)(e->k1_calls & 1ull);
             e->k1_calls++;
             q.stats_cur = e->d_k1_stats + 2 * par; q.stats_prev = e->d_k1_stats + 2 * (par ^ 1);
@@ -621,7 +650,12 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             // takes 115 % of the expected need and one top-up round follows (every round is three dependent launches);
             // the rare straggler goes to the monolithic kernel
             const bool few = n_slots < 128;
+            const bool fused_req = e->k1_fused != 0;
             if (few) q.first_frac = 1.15;
+            // speculative first round (k1_spec / k1_stitch): one stream generated window by window on many SMs; pays when a
+            // stream's first round is several windows long (>= 64 hypotheses per stream) and the GPU is otherwise idle
+            const int quota_max = (c.n_hyps + c.n_streams - 1) / c.n_streams;
+            const bool use_spec = few && off == 0 && n_slots <= e->k1_spec_slots && quota_max >= 64 && c.max_candidates >= (1 << 16) && !fused_req;   // (the candidate bound cannot fall inside the speculative round)
             const int n_rounds = (few && !e->k1_rounds_fixed) ? std::min(e->k1_rounds, 2) : e->k1_rounds;
             for (int r = 0; r < n_rounds; r++) {
                 // portions only pay when the generator has the whole GPU to fill (many streams); a few streams (single-frame
@@ -667,7 +701,16 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                     q.qidx = set;
                     q.fqidx = fset;
                     q.fq = e->d_k1_fq + (size_t)(fset & 1) * (size_t)n_slots_cap;
-                    launch_slot(q);
+                    if (use_spec && r == 0 && k == 0) {
+                        K1SpecParams spp;
+                        spp.vstate = e->d_k1_vstate; spp.vcells = e->d_k1_vcells; spp.vendw = e->d_k1_vendw; spp.result = e->d_k1_spec_result; spp.table = e->d_k1_spec_table;
+                        k1_spec<<<dim3(K1P_VPER, (unsigned)n_slots), K1S_THREADS, 0, stream>>>(q, spp);
+                        k1_stitch<<<(unsigned)n_slots, K1T_THREADS, 0, stream>>>(q, spp);
+                        k1_gather<<<dim3((unsigned)((e->k1_cap + K1G_PER_CTA - 1) / K1G_PER_CTA), (unsigned)n_slots), K1G_THREADS, 0, stream>>>(q, spp);
+                        e->launches += 2;
+                    } else {
+                        launch_slot(q);
+                    }
                     mark(0);
                     if (overlap) {
                         CU(cudaEventRecord(e->k1_ev_gen[set], stream));
@@ -682,7 +725,8 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                         CU(cudaEventRecord(e->k1_ev_filt[set], side));
                         CU(cudaStreamWaitEvent(solve_side, e->k1_ev_filt[set], 0));
                     }
-                    k1_solve<<<e->k1_solve_grid, K1V_THREADS, 0, solve_side>>>(q);
+                    if (few && e->k1_solve_group4) k1_solve4<<<e->k1_solve_grid, K1V_THREADS, 0, solve_side>>>(q);
+                    else k1_solve<<<e->k1_solve_grid, K1V_THREADS, 0, solve_side>>>(q);
                     if (solve_side != side) CU(cudaEventRecord(e->k1_ev_solve[set], solve_side));
                     if (!overlap) mark(2);
                     e->launches++;

@@ -61,6 +61,21 @@ DSAC_HD int mt_regenerate_words(const uint32_t* so, int t, uint32_t x[3]) {
     return 3;
 }
 
+// The same regeneration with the thread's own three words of the OLD state in registers (own[s] = old[t + 227 s]: they are
+// what the thread produced one regeneration earlier) and without a branch: all loads are issued first, the word after the
+// state's last one (needed by thread 169 only) is recomputed by every thread and selected.  A lone CTA twists a block in 230
+// cycles this way against 388 with mt_regenerate_words (tools/micro/twist_bench.cu).  x[2] is meaningful for t < 170.
+DSAC_HD void mt_twist3(const uint32_t* so, int t, const uint32_t own[3], uint32_t x[3]) {
+    const int k3 = (t + 2 * (MT_N - MT_M) < MT_N - 1) ? t + 2 * (MT_N - MT_M) : MT_N - 1;
+    const uint32_t a1 = so[t + 1], af = so[t + MT_M];
+    const uint32_t b1 = so[t + (MT_N - MT_M) + 1];
+    const uint32_t c1 = so[(k3 + 1 < MT_N - 1) ? k3 + 1 : MT_N - 1];
+    const uint32_t n0 = mt_twist(so[0], so[1], so[MT_M]);
+    x[0] = mt_twist(own[0], a1, af);
+    x[1] = mt_twist(own[1], b1, x[0]);
+    x[2] = mt_twist(own[2], (k3 == MT_N - 1) ? n0 : c1, x[1]);
+}
+
 // A window of tempered stream words addressed by absolute stream position.
 struct WordRing {
     const uint32_t* buf;

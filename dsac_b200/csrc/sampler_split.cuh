@@ -84,6 +84,7 @@ struct K1SplitParams {
     int wq_stride;
     int fqidx;                  // flag queue of this call: index into fq_n (the sets of a round may share one queue: one k1_solve per round)
     double first_frac;          // first round: this fraction of the expected need (K1S_FIRST_ROUND_FRAC; > 1 for few streams)
+    int spec;                   // 1: a speculative window of k1_spec (virtual slot: no work items, no accept bits, no statistics)
 };
 
 // ------------------------------------------------------------------ k1_cells
@@ -99,6 +100,17 @@ __global__ void __launch_bounds__(256) k1_cells(K1SplitParams q, int n_frames, i
         const int lane = (int)threadIdx.x, slot0 = (int)blockIdx.x * 32, slot = slot0 + lane;
         // stream s of global frame g: mt19937(seed + g*T + s)   (thread_rand.cpp:52 for g = 0)
         uint32_t v = p.seed + (uint32_t)(p.frame0 * (long long)p.T + slot);
+        if (q.n_slots < 32) {   // a few streams: nothing to coalesce, every stream stores its own words
+            if (slot < q.n_slots) {
+                uint32_t* mt = q.state[slot].mt;
+                mt[0] = v;
+                for (int i = 1; i < MT_N; i++) {
+                    v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
+                    mt[i] = v;
+                }
+            }
+            return;
+        }
         for (int i0 = 0; i0 < MT_N; i0 += 32) {
 #pragma unroll 8
             for (int j = 0; j < 32; j++) {
@@ -174,13 +186,16 @@ __device__ __forceinline__ int k1_round_size(int quota, int acc, long long cand_
 
 // The work of k1_slot for one (frame, stream), by a group of K1S_THREADS threads that synchronise with barrier BAR_ID
 // (0: the whole CTA of the k1_slot kernel; >= 1: the generator warps inside k1_fused).  tid: index within the group.
-template <int BAR_ID, int BAR_N, int NT>
-__device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmemT<NT / 32>& sm, const int tid, const int s, const int frame) {
+// TW3: regeneration through mt_twist3 (own words in registers, branch-free: fastest for a lone CTA -- 230 against 388 cycles per
+// block -- but ten instructions more per thread, which costs the issue-bound full batch 0.05 ms per step)
+template <int BAR_ID, int BAR_N, int NT, bool TW3 = (NT > 256)>
+__device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmemT<NT / 32>& sm, const int tid, const int s, const int frame,
+                                             const int slot_ov = -1) {
     constexpr int NW = NT / 32, SEL_WORDS = K1S_MAX_CAP / 32 / NT;   // warps of the group; accept-bit words per thread in the selection
     static_assert(SEL_WORDS >= 1 && K1S_LEFT_CAP % NT == 0, "k1_slot_body: thread count");
     const SampleParams& p = q.sp;
     const int lane = tid & 31, warp_id = tid >> 5;
-    const int slot = frame * p.T + s;
+    const int slot = (slot_ov >= 0) ? slot_ov : frame * p.T + s;   // slot_ov: a virtual slot of k1_spec (state / candidate arrays of its own)
     K1SlotState& S = q.state[slot];
     int h0, quota;
     stream_chunk(p.H, p.T, s, &h0, &quota);
@@ -308,6 +323,13 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmemT<NT
         group_barrier<BAR_ID, BAR_N>();
     }
 
+    // the thread's own three words of the current state, carried in registers from one regeneration to the next (mt_twist3)
+    uint32_t own[3] = {0u, 0u, 0u};
+    if (TW3 && tid < K1_WAVE) {
+        const uint32_t* half = sm.st + ((gen / MT_N) & 1u) * MT_N;
+        own[0] = half[tid]; own[1] = half[tid + K1_WAVE];
+        if (tid + 2 * K1_WAVE < MT_N) own[2] = half[tid + 2 * K1_WAVE];
+    }
     // ---------------- size of this round (first launch set of the round), size of this portion
     int round_total;
     if (q.gen_only) {
@@ -343,7 +365,14 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmemT<NT
             const bool all_in = base_off >= 0 && base_off + MT_N <= K1S_WORDS;   // the usual case: no per-word window test
             if (tid < K1_WAVE) {
                 uint32_t x[3];
-                const bool has3 = mt_regenerate_words(so, tid, x) == 3;
+                bool has3;
+                if (TW3) {
+                    mt_twist3(so, tid, own, x);
+                    own[0] = x[0]; own[1] = x[1]; own[2] = x[2];
+                    has3 = tid + 2 * K1_WAVE < MT_N;
+                } else {
+                    has3 = mt_regenerate_words(so, tid, x) == 3;
+                }
                 bool rej_any = false;
 #pragma unroll
                 for (int w = 0; w < 3; w++) {
@@ -573,14 +602,16 @@ __device__ __forceinline__ void k1_slot_body(const K1SplitParams& q, K1GSmemT<NT
         const uint32_t* half = sm.st + ((gen / MT_N) & 1u) * MT_N;
         for (int k = tid; k < MT_N; k += NT) S.mt[k] = half[k];
         for (int k = tid; k < left; k += NT) S.left[k] = sm.vals[k];
-        uint32_t* ab = q.accbits + (size_t)slot * (q.cap >> 5) + (already >> 5);   // `already` is a multiple of the chunk size
-        for (int k = tid; k < ((produced + 31) >> 5); k += NT) ab[k] = 0u;
+        if (!q.spec) {
+            uint32_t* ab = q.accbits + (size_t)slot * (q.cap >> 5) + (already >> 5);   // `already` is a multiple of the chunk size
+            for (int k = tid; k < ((produced + 31) >> 5); k += NT) ab[k] = 0u;
+        }
         if (tid == 0) {
             S.pos = pos; S.gen = gen; S.acc = acc; S.cand_base = cand_base; S.n_round = already + produced; S.done = 0;
             if (!q.gen_only) S.target = round_total;
             S.left_n = left; S.any_reject = sm.any_reject;
             if (q.round == 0 && !q.gen_only) S.overflow = 0;
-            const int n_items = (produced + q.chunk - 1) / q.chunk;
+            const int n_items = q.spec ? 0 : (produced + q.chunk - 1) / q.chunk;
             if (n_items > 0) {
                 const int at = atomicAdd(q.wq_n + q.qidx, n_items);
                 uint2* wq = q.wq + (size_t)q.qidx * q.wq_stride;
@@ -610,6 +641,279 @@ __global__ void __launch_bounds__(NT, (NT == K1S_THREADS) ? K1S_MIN_BLOCKS : 102
 __global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_slot(K1SplitParams q) {
     __shared__ K1GSmem sm;
     k1_slot_body<0, 0, K1S_THREADS>(q, sm, threadIdx.x, blockIdx.x, blockIdx.y);
+}
+
+// ------------------------------------------------------------------ k1_spec / k1_stitch: one stream generated by many CTAs
+// With a few streams (single-frame latency, BASELINE config 2) a stream's first round is one CTA's serial chain: ~280
+// MT19937 state regenerations and 11 windows of decode / scan / walk / write, 236 us for 21 946 candidates.  Here the round is
+// cut into windows of K1P_BLOCKS state blocks (W = 8 112 stream words); window j is generated by its own CTAs, which reach
+// their part of the stream by twisting the seeded state forward WITHOUT decoding (the cheap part of a regeneration) and
+// then run the ordinary generator (k1_slot_body) on a virtual slot for W / 8 + 32 candidates.  Where window j's first
+// candidate really starts is known only once window j-1 is parsed (a repeated cell shifts everything after it by two words), so
+// windows j >= 1 are generated for all four possible alignments (start = first word of the window + 0, 2, 4, 6 words: candidates
+// are sequences of (x, y) pairs, and every alignment falls into step with the true parse at the first candidate boundary it
+// shares with it).  k1_stitch then walks the windows in order -- true start of window j+1 = end of the last candidate of window j
+// that starts before it -- picks each window's alignment, checks that the boundary really is a candidate start there, and
+// gathers the chosen candidates into the stream's ordinary arrays, state and work items.  Any mismatch (a rejected Lemire draw,
+// a repeat inside the few candidates around a window boundary, a window too short) abandons the speculation: the stream is left
+// at its seeded state and the next, ordinary round generates it.  Same candidates, same order, same stream positions.
+constexpr int K1P_BLOCKS = 13;                          // state blocks per window
+constexpr int K1P_W = K1P_BLOCKS * MT_N;                // 8 112 stream words per window (a multiple of 8)
+constexpr int K1P_NW = K1P_W / 8 + 32;                  // candidates a window CTA generates: covers >= W + 256 words
+constexpr int K1P_CAPW = 2048;                          // candidate capacity of a virtual slot
+constexpr int K1P_MAX_WIN = 24;
+constexpr int K1P_VPER = 1 + 4 * (K1P_MAX_WIN - 1);     // virtual slots per stream
+constexpr int K1P_TABLE = 2 + 3 * K1P_MAX_WIN;
+constexpr int K1P_TAIL = 96;                            // stream positions staged from the end of every window's list
+static_assert(K1P_NW <= K1S_SR && K1P_NW <= K1P_CAPW && K1P_W % 8 == 0, "k1_spec window");
+
+struct K1SpecParams {
+    K1SlotState* vstate;   // [slots][K1P_VPER]
+    uint2* vcells;         // [slots][K1P_VPER][K1P_CAPW]
+    uint32_t* vendw;       // [slots][K1P_VPER][K1P_CAPW]
+    int* result;           // [slots] windows stitched (0: speculation abandoned) -- development aid
+    int* table;            // [slots][K1P_TABLE]: n_win, then per window (virtual slot, first candidate, base index), then the total: k1_stitch -> k1_gather
+};
+
+// windows of the speculative round: the first round's size as k1_round_size would choose it, in windows
+__device__ __forceinline__ int k1_spec_windows(const K1SplitParams& q, int quota) {
+    double prior = 0;
+    if (q.stats_prev && q.stats_prev[1] > 0) prior = (double)q.stats_prev[0] / (double)q.stats_prev[1];
+    const double n = q.first_frac * ((prior > 0) ? prior : 64.0) * quota;
+    int nw = (int)(n / (K1P_W / 8) + 0.5);
+    if (nw > K1P_MAX_WIN) nw = K1P_MAX_WIN;
+    if ((long long)nw * K1P_NW > (long long)q.cap) nw = q.cap / K1P_NW;
+    return nw < 2 ? 0 : nw;
+}
+
+__global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_spec(K1SplitParams q, K1SpecParams sp) {
+    __shared__ K1GSmem sm;
+    const SampleParams& p = q.sp;
+    const int tid = threadIdx.x, v = blockIdx.x, slot = blockIdx.y;
+    const int frame = slot / p.T, s = slot - frame * p.T;
+    int h0, quota;
+    stream_chunk(p.H, p.T, s, &h0, &quota);
+    if (quota == 0) return;
+    const int j = (v == 0) ? 0 : 1 + (v - 1) / 4, a = (v == 0) ? 0 : (v - 1) & 3;
+    if (j >= k1_spec_windows(q, quota)) return;
+    const uint32_t pos0 = (s == 0) ? p.skip : 0u;
+    const uint32_t pos_v = pos0 + (uint32_t)j * (uint32_t)K1P_W + 2u * (uint32_t)a;
+    const int n_skip = (int)(pos_v / MT_N);                 // state blocks before the one that holds pos_v
+    // the seeded state (k1_cells), twisted forward n_skip times: 227 threads, three dependent words each, raw state only
+    for (int k = tid; k < MT_N; k += K1S_THREADS) sm.st[k] = q.state[slot].mt[k];
+    __syncthreads();
+    uint32_t par = 0;
+    uint32_t own[3] = {0u, 0u, 0u};
+    if (tid < K1_WAVE) {
+        own[0] = sm.st[tid]; own[1] = sm.st[tid + K1_WAVE];
+        if (tid + 2 * K1_WAVE < MT_N) own[2] = sm.st[tid + 2 * K1_WAVE];
+    }
+    for (int it = 0; it < n_skip; it++) {
+        const uint32_t* so = sm.st + par * MT_N;
+        uint32_t* sn = sm.st + (par ^ 1u) * MT_N;
+        if (tid < K1_WAVE) {
+            uint32_t x[3];
+            mt_twist3(so, tid, own, x);
+            sn[tid] = x[0];
+            sn[tid + K1_WAVE] = x[1];
+            if (tid + 2 * K1_WAVE < MT_N) sn[tid + 2 * K1_WAVE] = x[2];
+            own[0] = x[0]; own[1] = x[1]; own[2] = x[2];
+        }
+        par ^= 1u;
+        __syncthreads();
+    }
+    const int vs = slot * K1P_VPER + v;
+    K1SlotState& Sv = sp.vstate[vs];
+    for (int k = tid; k < MT_N; k += K1S_THREADS) Sv.mt[k] = sm.st[par * MT_N + k];
+    if (tid == 0) {
+        Sv.pos = pos_v; Sv.gen = (uint32_t)n_skip * (uint32_t)MT_N; Sv.acc = 0; Sv.n_round = 0; Sv.done = 0; Sv.left_n = 0;
+        Sv.any_reject = 0; Sv.overflow = 0; Sv.target = 0; Sv.cand_base = 0;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // the ordinary generator on the virtual slot: "a later round with nothing to select" restores pos / gen / state from Sv
+    K1SplitParams qq = q;
+    qq.state = sp.vstate; qq.cells = sp.vcells; qq.endw = sp.vendw; qq.cap = K1P_CAPW;
+    qq.round = 1; qq.gen_only = 0; qq.select_only = 0; qq.portion = K1P_NW; qq.round_limit = K1P_NW; qq.spec = 1; qq.dbg = nullptr;
+    k1_slot_body<0, 0, K1S_THREADS, true>(qq, sm, tid, s, frame, vs);
+}
+
+struct K1StitchSmem {
+    uint32_t head[K1P_VPER][8];            // stream positions after the first 8 candidates of every window list
+    int n_list[K1P_VPER];                  // candidates in the list (0: unusable)
+    int c_list[K1P_VPER];                  // first candidate of the list that starts at or after the NEXT window (-1: not found in the staged tail)
+    uint32_t p_next[K1P_VPER];             // ... and where it starts
+    uint32_t start0[K1P_VPER];
+    int win_v[K1P_MAX_WIN], win_m[K1P_MAX_WIN], win_c[K1P_MAX_WIN], win_base[K1P_MAX_WIN + 1];
+    int n_win, ok, wq_at;
+};
+
+constexpr int K1T_THREADS = 1024;
+__global__ void __launch_bounds__(K1T_THREADS) k1_stitch(K1SplitParams q, K1SpecParams sp) {
+    __shared__ K1StitchSmem sm;
+    const SampleParams& p = q.sp;
+    const int tid = threadIdx.x, slot = blockIdx.x;
+    const int frame = slot / p.T, s = slot - frame * p.T;
+    int h0, quota;
+    stream_chunk(p.H, p.T, s, &h0, &quota);
+    K1SlotState& S = q.state[slot];
+    if (quota == 0) {
+        if (tid == 0) {
+            S.done = 1; S.acc = 0; S.n_round = 0; S.target = 0; S.cand_base = 0; S.left_n = 0; S.any_reject = 0; S.overflow = 0; S.pos = 0; S.gen = 0;
+            p.stream_ncand[slot] = 0;
+            p.stream_endpos[slot] = 0;
+        }
+        return;
+    }
+    const int n_win = k1_spec_windows(q, quota);
+    const uint32_t pos0 = (s == 0) ? p.skip : 0u;
+    const int n_virt = n_win > 0 ? 1 + 4 * (n_win - 1) : 0;
+    const size_t vbase = (size_t)slot * K1P_VPER;
+    // per window list, one warp each (all lists in parallel, coalesced): its length, its first 8 stream positions, and the first
+    // candidate that starts at or after the next window (searched in the last K1P_TAIL entries: candidate nl - TAIL + t + 1 starts
+    // at entry nl - TAIL + t) -- neither depends on where the list is entered, so the chain below is table look-ups only
+    {
+        const uint32_t FULL = 0xffffffffu;
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int v = warp; v < n_virt; v += K1T_THREADS / 32) {
+            const K1SlotState& Sv = sp.vstate[vbase + v];
+            int nl = min(max(Sv.n_round, 0), K1P_CAPW);
+            if (Sv.any_reject || Sv.overflow || nl < K1P_TAIL + 8) nl = 0;
+            const int jv = (v == 0) ? 0 : 1 + (v - 1) / 4, av = (v == 0) ? 0 : (v - 1) & 3;
+            const uint32_t Onext = pos0 + (uint32_t)(jv + 1) * (uint32_t)K1P_W;
+            const uint32_t* ew = sp.vendw + (vbase + v) * K1P_CAPW;
+            int tc = -1;
+            uint32_t pn = 0u;
+            if (nl > 0) {
+                if (lane < 8) sm.head[v][lane] = ew[lane];
+#pragma unroll
+                for (int t0 = 0; t0 < K1P_TAIL; t0 += 32) {
+                    const uint32_t val = ew[nl - K1P_TAIL + t0 + lane];
+                    const uint32_t over = __ballot_sync(FULL, val >= Onext);
+                    if (tc < 0 && over) {
+                        const int l = __ffs(over) - 1;
+                        tc = t0 + l;
+                        pn = __shfl_sync(FULL, val, l);
+                    }
+                }
+            }
+            if (lane == 0) {
+                sm.n_list[v] = nl;
+                // tc == 0: the crossing may lie before the staged tail; tc < 0: the list ends before the next window
+                const int c = (tc > 0) ? nl - K1P_TAIL + tc + 1 : -1;
+                sm.c_list[v] = (c > 0 && c < nl) ? c : -1;
+                sm.p_next[v] = pn;
+                sm.start0[v] = pos0 + (uint32_t)jv * (uint32_t)K1P_W + 2u * (uint32_t)av;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {   // the chain over the windows
+        int ok = n_win >= 2, base = 0;
+        uint32_t P = pos0;                       // true start of the current window's first candidate
+        for (int j = 0; j < n_win && ok; j++) {
+            const uint32_t O = pos0 + (uint32_t)j * (uint32_t)K1P_W;
+            const uint32_t rel = P - O;
+            if (P < O || (rel & 1u)) { ok = 0; break; }
+            const int a = (int)((rel >> 1) & 3u), v = (j == 0) ? 0 : 1 + 4 * (j - 1) + a;
+            if (j == 0 && a != 0) { ok = 0; break; }
+            const int nl = sm.n_list[v];
+            if (nl <= 0) { ok = 0; break; }
+            // m: the candidate of this list that starts at P (start_0 = the list's own start, start_i = position after i-1)
+            int m = -1;
+            if (sm.start0[v] == P) m = 0;
+            else
+                for (int i = 0; i < 8; i++)
+                    if (sm.head[v][i] == P) { m = i + 1; break; }
+            if (m < 0) { ok = 0; break; }
+            int c = nl;                          // one past the last candidate taken from this window
+            if (j + 1 < n_win) {
+                c = sm.c_list[v];
+                if (c < 0 || c <= m) { ok = 0; break; }
+                P = sm.p_next[v];
+            }
+            sm.win_v[j] = v; sm.win_m[j] = m; sm.win_c[j] = c; sm.win_base[j] = base;
+            base += c - m;
+        }
+        if (ok && base > q.cap) ok = 0;
+        sm.win_base[n_win > 0 ? n_win : 0] = base;
+        sm.n_win = n_win; sm.ok = ok;
+    }
+    __syncthreads();
+    const size_t cbase = (size_t)slot * q.cap;
+    if (!sm.ok) {
+        // speculation abandoned: the stream stands at its seeded state, the next (ordinary) round generates it
+        if (tid == 0) {
+            S.pos = pos0; S.gen = 0; S.acc = 0; S.cand_base = 0; S.n_round = 0; S.target = 0; S.done = 0; S.left_n = 0;
+            S.any_reject = 0; S.overflow = 0;
+            if (sp.result) sp.result[slot] = 0;
+            sp.table[(size_t)slot * K1P_TABLE] = 0;
+            sp.table[(size_t)slot * K1P_TABLE + 1] = 0;
+        }
+        return;
+    }
+    const int n_total = sm.win_base[sm.n_win];
+    {   // the window table for k1_gather (which copies the chosen candidates on many SMs)
+        int* tb = sp.table + (size_t)slot * K1P_TABLE;
+        if (tid == 0) { tb[0] = sm.n_win; tb[1] = n_total; }
+        if (tid < sm.n_win) { tb[2 + 3 * tid] = sm.win_v[tid]; tb[3 + 3 * tid] = sm.win_m[tid]; tb[4 + 3 * tid] = sm.win_base[tid]; }
+    }
+    {
+        const K1SlotState& Sl = sp.vstate[vbase + sm.win_v[sm.n_win - 1]];   // the last window ran to its own end: its state is the round's
+        for (int k = tid; k < MT_N; k += K1T_THREADS) S.mt[k] = Sl.mt[k];
+        const int ln = min(max(Sl.left_n, 0), K1S_LEFT_CAP);
+        for (int k = tid; k < ln; k += K1T_THREADS) S.left[k] = Sl.left[k];
+        uint32_t* ab = q.accbits + (size_t)slot * (q.cap >> 5);
+        for (int k = tid; k < ((n_total + 31) >> 5); k += K1T_THREADS) ab[k] = 0u;
+        {   // filter work items of the round
+            const int n_items = (n_total + q.chunk - 1) / q.chunk;
+            if (tid == 0) sm.wq_at = atomicAdd(q.wq_n + q.qidx, n_items);
+            __syncthreads();
+            uint2* wq = q.wq + (size_t)q.qidx * q.wq_stride + sm.wq_at;
+            for (int c = tid; c < n_items; c += K1T_THREADS)
+                wq[c] = make_uint2((uint32_t)slot * 128u + (uint32_t)c, (uint32_t)min(q.chunk, n_total - c * q.chunk));
+        }
+        if (tid == 0) {
+            S.pos = Sl.pos; S.gen = Sl.gen; S.acc = 0; S.cand_base = 0; S.n_round = n_total; S.target = n_total; S.done = 0;
+            S.left_n = ln; S.any_reject = Sl.any_reject; S.overflow = 0;
+            if (q.dbg) {
+                atomicAdd(q.dbg + 0, 1ull);
+                atomicAdd(q.dbg + 1, (unsigned long long)n_total);
+            }
+            if (sp.result) sp.result[slot] = sm.n_win;
+        }
+    }
+}
+
+// copies the candidates k1_stitch chose from the window lists into the stream's ordinary arrays (blockIdx.y: stream)
+constexpr int K1G_THREADS = 256, K1G_PER_CTA = 1024;
+__global__ void __launch_bounds__(K1G_THREADS) k1_gather(K1SplitParams q, K1SpecParams sp) {
+    __shared__ int tb[K1P_TABLE];
+    const int slot = blockIdx.y, tid = threadIdx.x;
+    if (tid < K1P_TABLE) tb[tid] = sp.table[(size_t)slot * K1P_TABLE + tid];
+    __syncthreads();
+    const int n_win = tb[0], n_total = tb[1];
+    const int g0 = blockIdx.x * K1G_PER_CTA;
+    if (n_win <= 0 || g0 >= n_total) return;
+    const size_t cbase = (size_t)slot * q.cap, vbase = (size_t)slot * K1P_VPER;
+    uint2 c[K1G_PER_CTA / K1G_THREADS];
+    uint32_t e[K1G_PER_CTA / K1G_THREADS];
+#pragma unroll
+    for (int k = 0; k < K1G_PER_CTA / K1G_THREADS; k++) {
+        const int g = g0 + tid + k * K1G_THREADS;
+        if (g < n_total) {
+            int j = 0;
+            while (j + 1 < n_win && tb[4 + 3 * (j + 1)] <= g) j++;
+            const size_t src = (vbase + tb[2 + 3 * j]) * K1P_CAPW + (size_t)(tb[3 + 3 * j] + (g - tb[4 + 3 * j]));
+            c[k] = sp.vcells[src];
+            e[k] = sp.vendw[src];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K1G_PER_CTA / K1G_THREADS; k++) {
+        const int g = g0 + tid + k * K1G_THREADS;
+        if (g < n_total) { q.cells[cbase + g] = c[k]; q.endw[cbase + g] = e[k]; }
+    }
 }
 
 // ------------------------------------------------------------------ k1_filter
@@ -784,10 +1088,11 @@ __global__ void __launch_bounds__(K1X_THREADS, 1) k1_fused(K1SplitParams qf, K1S
 #ifndef K1V_MIN_BLOCKS
 #define K1V_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(K1V_THREADS, K1V_MIN_BLOCKS) k1_solve(K1SplitParams q) {
+template <int GROUP>
+__device__ __forceinline__ void k1_solve_body(const K1SplitParams& q) {
     const SampleParams& p = q.sp;
     const int tid = threadIdx.x;
-    constexpr int GROUP = K1V_GROUP, GROUPS = K1V_THREADS / GROUP, ROOTS = 4 / GROUP;
+    constexpr int GROUPS = K1V_THREADS / GROUP, ROOTS = 4 / GROUP;
     const int n_q = q.fq_n[q.fqidx];
     const int sub = tid % GROUP;
     for (int base = blockIdx.x * GROUPS; base < n_q; base += gridDim.x * GROUPS) {
@@ -842,5 +1147,11 @@ __global__ void __launch_bounds__(K1V_THREADS, K1V_MIN_BLOCKS) k1_solve(K1SplitP
         }
     }
 }
+
+// one thread per flagged candidate when there are many (a full batch: fewer, fuller warps), four lanes per candidate -- one quartic
+// root each, the same minimum with the same tie rule -- when there are few (single-frame latency: the launch lasts as long as one
+// candidate's chain, and the four roots are that chain's longest part)
+__global__ void __launch_bounds__(K1V_THREADS, K1V_MIN_BLOCKS) k1_solve(K1SplitParams q) { k1_solve_body<K1V_GROUP>(q); }
+__global__ void __launch_bounds__(K1V_THREADS, K1V_MIN_BLOCKS) k1_solve4(K1SplitParams q) { k1_solve_body<4>(q); }
 
 }  // namespace dsac

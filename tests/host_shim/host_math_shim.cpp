@@ -248,5 +248,26 @@ extern "C" void shim_mt_regenerated(uint32_t seed, int n_blocks, uint32_t* out) 
     }
 }
 
+// the register-carried, branch-free form of the same regeneration (mt_twist3: k1_slot / k1_spec)
+extern "C" void shim_mt_twist3(uint32_t seed, int n_blocks, uint32_t* out) {
+    uint32_t st[2 * dsac::MT_N];
+    dsac::mt_seed(st, seed);
+    const int W = dsac::MT_N - dsac::MT_M;
+    uint32_t own[W][3];
+    for (int t = 0; t < W; t++)
+        for (int w = 0; w < 3; w++) own[t][w] = (t + w * W < dsac::MT_N) ? st[t + w * W] : 0u;
+    for (int r = 0; r < n_blocks; r++) {
+        const uint32_t* so = st + (r & 1) * dsac::MT_N;
+        uint32_t* sn = st + ((r & 1) ^ 1) * dsac::MT_N;
+        for (int t = W - 1; t >= 0; t--) {
+            uint32_t x[3];
+            dsac::mt_twist3(so, t, own[t], x);
+            for (int w = 0; w < 3; w++)
+                if (t + w * W < dsac::MT_N) { sn[t + w * W] = x[w]; own[t][w] = x[w]; }
+        }
+        for (int k = 0; k < dsac::MT_N; k++) out[r * dsac::MT_N + k] = dsac::mt_temper(sn[k]);
+    }
+}
+
 // k_sample's pair-based candidate parser (windows without rejected draws) against the reference loop on the same pairs
 extern "C" int shim_cand_pairs_len(const unsigned short* pr16, int sp, int limit) { return dsac::cand_pairs_len(pr16, sp, limit); }

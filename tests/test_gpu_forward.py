@@ -60,6 +60,31 @@ def test_forward_matches_oracle(engine_mod, oracle, T, H):
     eng.close()
 
 
+@pytest.mark.parametrize("T,nf", [(1, 1), (1, 3), (2, 2), (3, 1)])
+def test_speculative_first_round_is_scheduling_only(engine_mod, oracle, T, nf, monkeypatch):
+    """k1_spec / k1_stitch / k1_gather (a few streams: the first round generated window by window on many SMs, four alignments
+    per window, stitched afterwards) must give exactly the candidates of the one-CTA-per-stream generator -- and the oracle's."""
+    E, O = engine_mod, oracle
+    H = 256
+    coords, pix, gt_cv, gt_jp = E.synth_frames(nf, n_streams=T)
+    out = {}
+    for spec in ("1", "0"):
+        monkeypatch.setenv("DSAC_K1_SPEC", spec)
+        eng = E.Engine(max_frames=nf, n_streams=T, n_hyps=H)
+        l0 = eng.launches
+        res = eng.forward(coords, pix, gt_jp)
+        out[spec] = (res, eng.launches - l0)
+        eng.close()
+    a, b = out["1"][0], out["0"][0]
+    assert out["1"][1] > out["0"][1]                     # the speculative path really ran (three more launches in round 0)
+    for name in ("img_idx", "cand_idx", "n_candidates", "hyp_pose", "scores", "ref_pose", "inlier_map", "status"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    for f in range(nf):
+        fw = _oracle_frame(O, dict(n_hyps=H), coords[f], pix[f], gt_jp[f], f, T)
+        assert np.array_equal(fw.img_idx, a.img_idx[f]) and np.array_equal(fw.cand_idx, a.cand_idx[f])
+        assert fw.n_candidates == a.n_candidates[f]
+
+
 @pytest.mark.parametrize("threads", [256, 512, 1024])
 def test_generator_thread_counts_sample_the_same_sets(engine_mod, oracle, threads, monkeypatch):
     """k1_slot is instantiated for 256 / 512 / 1024 threads per (frame, stream) and chosen by the number of streams

@@ -70,6 +70,15 @@ def test_block_parallel_mt19937_regeneration_matches_std(oracle, host_shim):
         assert np.array_equal(out, oracle.mt19937_raw(seed, 5 * 624))
 
 
+def test_register_carried_regeneration_matches_std(oracle, host_shim):
+    """mt_twist3 (the generator's and k1_spec's form of the regeneration: own words in registers, no branch) gives the same
+    stream as std::mt19937."""
+    for seed in (1305, 1306, 5489, 0xffffffff):
+        out = np.zeros(7 * 624, np.uint32)
+        host_shim.shim_mt_twist3(C.c_uint32(seed), 7, oracle._p(out))
+        assert np.array_equal(out, oracle.mt19937_raw(seed, 7 * 624))
+
+
 def test_pair_based_candidate_parser(host_shim):
     """cand_pairs_len (k_sample's boundary walk): number of (x, y) pairs a minimal set consumes = pairs drawn until four
     distinct cells are found (cnn_softam.h:1021-1039), incl. repeated cells, long runs of repeats and the end of the window."""
