@@ -484,7 +484,7 @@ def main():
         for T in (1, 8):
             med, p10, p90 = frame_latency(H, T, E.STAGE_SAMPLE | E.STAGE_SCORE)
             single["streams_%d" % T] = {"latency_us": med, "p10_us": p10, "p90_us": p90, "hyp_per_s": H / (med * 1e-6)}
-        single["bound"] = "latency: one stream is one generator CTA -- 282 serial MT19937 state regenerations + 11 windows of scan / walk / write (DESIGN.md section 9)"
+        single["bound"] = "latency: one stream's first round is generated window by window on many SMs (k1_spec: twist-ahead, four alignments per window, stitched afterwards); what remains serial is the MT19937 twist chain to the last window, then stitch, filter, solve (DESIGN.md section 5)"
         # config 1: the reference's own CPU-runnable case (1 frame, 64 hypotheses, full test pipeline)
         med1, p10_1, p90_1 = frame_latency(64, 1, E.STAGE_ALL)
         config1 = {"workload": "config 1: 1 frame x 64 hyp x 1600 pts, full test pipeline (sample+score+softargmax+refine+eval)",

@@ -20,7 +20,7 @@ ST_SAMPLER_EXHAUSTED, ST_REFINE_ABORTED = 1, 2
 EXPORTS = [
     "dsac_default_config", "dsac_engine_create", "dsac_engine_destroy", "dsac_last_error", "dsac_engine_config",
     "dsac_forward", "dsac_forward_submit", "dsac_forward_wait", "dsac_forward_device", "dsac_fetch", "dsac_device_view_get", "dsac_set_stages",
-    "dsac_set_tail_split", "dsac_launch_count", "dsac_sampler_profile", "dsac_sampler_profile_read", "dsac_set_score_hook", "dsac_set_score_backward_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_gather_patches_device", "dsac_coords_from_prediction_device", "dsac_kabsch",
+    "dsac_set_tail_split", "dsac_launch_count", "dsac_sampler_profile", "dsac_sampler_profile_read", "dsac_debug_spec_result", "dsac_set_score_hook", "dsac_set_score_backward_hook", "dsac_backward", "dsac_forward_dsac", "dsac_backward_dsac", "dsac_gather_patches_device", "dsac_coords_from_prediction_device", "dsac_kabsch",
     "dsac_stochastic_subsample",
     "dsac_synth_frames", "dsac_version",
 ]
@@ -107,6 +107,7 @@ def load(build_if_missing=True):
     lib.dsac_device_view_get.argtypes = [C.c_void_p, C.POINTER(DeviceView)]
     lib.dsac_sampler_profile.argtypes = [C.c_void_p, C.c_int32]
     lib.dsac_sampler_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dsac_debug_spec_result.argtypes = [C.c_void_p, C.c_void_p]
     lib.dsac_set_stages.argtypes = [C.c_void_p, C.c_uint32]
     lib.dsac_set_tail_split.argtypes = [C.c_void_p, C.c_int32]
     lib.dsac_set_score_hook.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -282,6 +283,12 @@ class Engine:
         cnt = (C.c_uint64 * 4)()
         self._check(self.lib.dsac_sampler_profile_read(self.h, ms, cnt))
         return list(ms), [int(x) for x in cnt]
+
+    def spec_result(self):
+        """Windows stitched per stream by the speculative first round of the last pass (0: abandoned / not used)."""
+        out = (C.c_int32 * 8)()
+        self._check(self.lib.dsac_debug_spec_result(self.h, out))
+        return [int(x) for x in out]
 
     def set_tail_split(self, mode):
         """0: off, 1: forward_device + blocking forward (default), 2: submitted passes too (scheduling only)."""

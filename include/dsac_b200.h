@@ -168,6 +168,9 @@ int64_t dsac_launch_count(const dsac_engine* e);
  *   counts[0..3] candidates generated, candidates flagged by the filter, candidates accepted, rounds that had work. */
 int dsac_sampler_profile(dsac_engine* e, int32_t enable);
 int dsac_sampler_profile_read(dsac_engine* e, double ms[4], uint64_t counts[4]);
+/* Development aid: per stream (first 8 of the last pass), the number of windows the speculative first round of a few streams
+ * (k1_spec / k1_stitch) stitched; 0 = speculation abandoned (the ordinary round generated the stream) or not used. */
+int dsac_debug_spec_result(dsac_engine* e, int32_t out8[8]);
 
 /* Score seam: replaces forward(diffMaps, stateObj) (lua_calls.h:284-300; call site
  * cnn_softam.h:1072).  If set, the engine materialises the diffmaps and calls the hook with

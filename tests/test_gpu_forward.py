@@ -60,7 +60,7 @@ def test_forward_matches_oracle(engine_mod, oracle, T, H):
     eng.close()
 
 
-@pytest.mark.parametrize("T,nf", [(1, 1), (1, 3), (2, 2), (3, 1)])
+@pytest.mark.parametrize("T,nf", [(1, 1), (1, 3), (2, 2), (3, 1), (1, 8)])
 def test_speculative_first_round_is_scheduling_only(engine_mod, oracle, T, nf, monkeypatch):
     """k1_spec / k1_stitch / k1_gather (a few streams: the first round generated window by window on many SMs, four alignments
     per window, stitched afterwards) must give exactly the candidates of the one-CTA-per-stream generator -- and the oracle's."""
