@@ -337,27 +337,31 @@ def main():
         step_host()
     torch.cuda.synchronize()
     sync_s = time.perf_counter() - t0
-    # (b) the driver loop with two engines in flight (dsac_forward_submit / dsac_forward_wait): every step still copies its
-    # inputs from pinned host memory and reads its results back, but the copies of one step overlap the kernels of the other
-    eng_b = E.Engine(max_frames=nf, device=local_rank)
-    engs = (eng, eng_b)
-    outs = (out, host_result()[0])
+    # (b) the driver loop with DEPTH engines in flight (dsac_forward_submit / dsac_forward_wait): every step still copies its
+    # inputs from pinned host memory and reads its results back, but the copies of one step overlap the kernels of the others
+    # (measured, tools/e2e_depth_probe.py: 1 / 2 / 3 / 4 engines in flight 4.21 / 2.74 / 2.60 / 2.59 ms per step)
+    DEPTH = 3
+    engs = [eng] + [E.Engine(max_frames=nf, device=local_rank) for _ in range(DEPTH - 1)]
+    outs = [out] + [host_result()[0] for _ in range(DEPTH - 1)]
 
     def run_pipelined(steps):
         for i in range(steps):
-            engs[i & 1].forward_wait()
-            engs[i & 1].forward_submit(h_coords, h_pix, h_gt, frame0=frame0, out=outs[i & 1])
-        engs[0].forward_wait(); engs[1].forward_wait()
+            engs[i % DEPTH].forward_wait()
+            engs[i % DEPTH].forward_submit(h_coords, h_pix, h_gt, frame0=frame0, out=outs[i % DEPTH])
+        for e_ in engs:
+            e_.forward_wait()
 
-    run_pipelined(max(args.warmup, 3) + 1)
+    run_pipelined(max(args.warmup, 3) + DEPTH)
     barrier()
     t0 = time.perf_counter()
     run_pipelined(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
-    assert np.array_equal(outs[0].correct, outs[1].correct) and np.array_equal(outs[0].ref_pose, outs[1].ref_pose)
-    eng_b.close()
+    for o_ in outs[1:]:
+        assert np.array_equal(outs[0].correct, o_.correct) and np.array_equal(outs[0].ref_pose, o_.ref_pose)
+    for e_ in engs[1:]:
+        e_.close()
     t = torch.tensor([e2e_s, sync_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -625,10 +629,10 @@ def main():
                        "l2": "256 MB buffer written between timed steps (flush); each step also streams %.2f GB of diffmaps" % (BYTES_M * nf / 1e9)},
             "e2e": {"value": e2e_value, "unit": "hyp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(t[0].item()) / args.steps,
-                    "api": "dsac_forward_submit / dsac_forward_wait, two engines in flight on the GPU (the driver's frame loop): every step "
+                    "api": "dsac_forward_submit / dsac_forward_wait, three engines in flight on the GPU (the driver's frame loop): every step "
                            "copies its inputs from pinned host buffers (H2D) and reads poses/scores/errors back (D2H); the copies of one "
                            "step overlap the kernels of the other",
-                    "pipeline_depth": 2,
+                    "pipeline_depth": 3,
                     "note": "can exceed `value`: consecutive steps overlap on the GPU (the last, partial wave of one step's sampler is "
                             "filled by the other engine's kernels), which the per-step-isolated, L2-flushed `value` measurement forbids",
                     "sync_call": {"value": e2e_sync_value, "ms_per_step": 1e3 * float(t[1].item()) / args.steps,
