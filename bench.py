@@ -360,6 +360,28 @@ def main():
     barrier()
     for o_ in outs[1:]:
         assert np.array_equal(outs[0].correct, o_.correct) and np.array_equal(outs[0].ref_pose, o_.ref_pose)
+    # (c) for information: the same DEPTH engines on DEVICE-resident inputs, consecutive steps in flight on DEPTH streams (no
+    # host copies, no L2 flush: every step streams 1.7 GB of diffmaps, far more than the 126 MB L2) -- the steady-state
+    # throughput of the kernels alone, between the step-isolated `value` and `e2e`
+    pstreams = [torch.cuda.Stream(device=local_rank) for _ in range(DEPTH)]
+
+    def run_device_pipelined(steps):
+        for i in range(steps):
+            engs[i % DEPTH].forward_device(nf, d_coords.data_ptr(), d_pix.data_ptr(), 0, d_gt.data_ptr(), frame0, pstreams[i % DEPTH].cuda_stream)
+
+    run_device_pipelined(2 * DEPTH)
+    barrier()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for st_ in pstreams:
+        st_.wait_event(pe0)
+    run_device_pipelined(args.steps)
+    for st_ in pstreams:
+        torch.cuda.current_stream().wait_stream(st_)
+    pe1.record()
+    pe1.synchronize()
+    dev_pipe_ms = pe0.elapsed_time(pe1) / args.steps
+    barrier()
     for e_ in engs[1:]:
         e_.close()
     t = torch.tensor([e2e_s, sync_s], dtype=torch.float64, device="cuda")
@@ -633,6 +655,8 @@ def main():
                            "copies its inputs from pinned host buffers (H2D) and reads poses/scores/errors back (D2H); the copies of one "
                            "step overlap the kernels of the other",
                     "pipeline_depth": 3,
+                    "device_resident_pipelined": {"ms_per_step": dev_pipe_ms, "value": nf * H / (dev_pipe_ms * 1e-3) * world, "unit": "hyp/s",
+                                                  "note": "for information: the same three engines on device-resident inputs, consecutive steps in flight on three streams (no host copies); rank 0's time"},
                     "note": "can exceed `value`: consecutive steps overlap on the GPU (the last, partial wave of one step's sampler is "
                             "filled by the other engine's kernels), which the per-step-isolated, L2-flushed `value` measurement forbids",
                     "sync_call": {"value": e2e_sync_value, "ms_per_step": 1e3 * float(t[1].item()) / args.steps,
