@@ -125,6 +125,15 @@ struct dsac_engine {
     cudaEvent_t k1_ev_solve[K1S_MAX_SETS] = {};   // solve of launch set i done
     cudaEvent_t k1_ev_gen[K1S_MAX_SETS] = {};     // generation of launch set i done
     cudaEvent_t k1_ev_round = nullptr;            // last solve of a round done
+    // a second, independent set of the per-pass sampler resources: a large batch runs as two concurrent half-batches (forward_split)
+    struct K1Lane {
+        cudaStream_t main = nullptr, side = nullptr, side2 = nullptr;
+        cudaEvent_t ev_filt[K1S_MAX_SETS] = {}, ev_solve[K1S_MAX_SETS] = {}, ev_gen[K1S_MAX_SETS] = {}, ev_round = nullptr;
+        int* counters = nullptr;
+        unsigned long long* stats = nullptr;
+        unsigned long long calls = 0;
+    } lane1;
+    int k1_lanes = 1;                             // DSAC_K1_LANES: 0 = never split a batch into two lanes
     int k1_overlap = 1;
     bool k1_overlap_fixed = false;                // DSAC_K1_OVERLAP given
     int k1_solve_batch = 0;                       // 1: one k1_solve per round over the flagged candidates of all its launch sets (measured SLOWER, 3.07 vs 2.92 ms per step: a per-set solve runs beside the next set's generator, a per-round one runs alone)
@@ -233,6 +242,18 @@ void dsac_engine_destroy(dsac_engine* e) {
     for (cudaEvent_t ev : e->k1_ev_solve) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->k1_ev_gen) if (ev) cudaEventDestroy(ev);
     if (e->k1_ev_round) cudaEventDestroy(e->k1_ev_round);
+    {
+        dsac_engine::K1Lane& L = e->lane1;
+        for (cudaStream_t st : {L.main, L.side, L.side2}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        for (int i = 0; i < K1S_MAX_SETS; i++) {
+            if (L.ev_filt[i]) cudaEventDestroy(L.ev_filt[i]);
+            if (L.ev_solve[i]) cudaEventDestroy(L.ev_solve[i]);
+            if (L.ev_gen[i]) cudaEventDestroy(L.ev_gen[i]);
+        }
+        if (L.ev_round) cudaEventDestroy(L.ev_round);
+        if (L.counters) cudaFree(L.counters);
+        if (L.stats) cudaFree(L.stats);
+    }
     void* k1ptrs[] = {e->d_k1_spec_table, e->d_k1_vstate, e->d_k1_vcells, e->d_k1_vendw, e->d_k1_spec_result, e->d_k1_state, e->d_k1_celltab, e->d_k1_cells, e->d_k1_endw, e->d_k1_accbits, e->d_k1_pose, e->d_k1_wq,
                       e->d_k1_fq, e->d_k1_counters, e->d_k1_stats, e->d_k1_dbg};
     for (void* p : k1ptrs)
@@ -404,6 +425,24 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         }
         for (int i = 0; i < K1S_MAX_SETS; i++) CUC(cudaEventCreateWithFlags(&e->k1_ev_gen[i], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&e->k1_ev_round, cudaEventDisableTiming));
+        {   // the second lane (forward_split: two concurrent half-batches)
+            int least = 0, greatest = 0;
+            CUC(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            dsac_engine::K1Lane& L = e->lane1;
+            CUC(cudaStreamCreateWithFlags(&L.main, cudaStreamNonBlocking));
+            CUC(cudaStreamCreateWithPriority(&L.side, cudaStreamNonBlocking, greatest));
+            CUC(cudaStreamCreateWithPriority(&L.side2, cudaStreamNonBlocking, greatest));
+            for (int i = 0; i < K1S_MAX_SETS; i++) {
+                CUC(cudaEventCreateWithFlags(&L.ev_filt[i], cudaEventDisableTiming));
+                CUC(cudaEventCreateWithFlags(&L.ev_solve[i], cudaEventDisableTiming));
+                CUC(cudaEventCreateWithFlags(&L.ev_gen[i], cudaEventDisableTiming));
+            }
+            CUC(cudaEventCreateWithFlags(&L.ev_round, cudaEventDisableTiming));
+            CUC(cudaMalloc(&L.counters, 2 * K1S_MAX_SETS * sizeof(int)));
+            CUC(cudaMalloc(&L.stats, 4 * sizeof(unsigned long long)));
+            CUC(cudaMemset(L.stats, 0, 4 * sizeof(unsigned long long)));
+            if (const char* ln = getenv("DSAC_K1_LANES")) e->k1_lanes = atoi(ln);
+        }
         if (const char* ov = getenv("DSAC_K1_OVERLAP")) { e->k1_overlap = atoi(ov); e->k1_overlap_fixed = true; }
         if (const char* fu = getenv("DSAC_K1_FUSED")) e->k1_fused = atoi(fu);
         if (const char* stt = getenv("DSAC_K1_SLOT_THREADS")) e->k1_slot_threads = atoi(stt);
@@ -550,7 +589,7 @@ static int pick_tile(const dsac_engine* e, int n_frames) {
 // Launches the forward stages for `n` frames whose per-frame engine buffers start at frame offset `off`
 // (inputs are passed already offset).  Used whole (off = 0) and per chunk by the pipelined host path.
 static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0, const int16_t* d_coords, const int32_t* d_pix,
-                         int32_t pix_shared, const double* d_gt_jp, void* stream_v) {
+                         int32_t pix_shared, const double* d_gt_jp, void* stream_v, int lane = 0) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     const dsac_config& c = e->cfg;
     const size_t o = (size_t)off, Hh = (size_t)c.n_hyps, Nn = DSAC_N;
@@ -575,19 +614,28 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
         } else {
             // round-based pipeline (sampler_split.cuh).  One pass at a time per engine: the queues are shared.
             const size_t T = (size_t)c.n_streams, cap = (size_t)e->k1_cap;
+            // the lane's own streams, events, counters and statistics (lane 0: the engine's; lane 1: e->lane1)
+            cudaStream_t k_side = lane ? e->lane1.side : e->k1_side, k_side2 = lane ? e->lane1.side2 : e->k1_side2;
+            cudaEvent_t* k_ev_filt = lane ? e->lane1.ev_filt : e->k1_ev_filt;
+            cudaEvent_t* k_ev_solve = lane ? e->lane1.ev_solve : e->k1_ev_solve;
+            cudaEvent_t* k_ev_gen = lane ? e->lane1.ev_gen : e->k1_ev_gen;
+            cudaEvent_t k_ev_round = lane ? e->lane1.ev_round : e->k1_ev_round;
+            int* k_counters = lane ? e->lane1.counters : e->d_k1_counters;
+            unsigned long long* k_stats = lane ? e->lane1.stats : e->d_k1_stats;
+            unsigned long long& k_calls = lane ? e->lane1.calls : e->k1_calls;
             K1SplitParams q;
             q.sp = sp;
             q.state = e->d_k1_state + o * T; q.celltab = e->d_k1_celltab + o * Nn;
             q.cells = e->d_k1_cells + o * T * cap; q.endw = e->d_k1_endw + o * T * cap;
             q.accbits = e->d_k1_accbits + o * T * (cap / 32); q.pose_out = e->d_k1_pose + o * T * cap * 6;
-            q.wq = e->d_k1_wq; q.fq = e->d_k1_fq;
-            q.wq_n = e->d_k1_counters; q.fq_n = e->d_k1_counters + K1S_MAX_SETS;
+            q.wq = e->d_k1_wq + o * T * 128; q.fq = e->d_k1_fq + o * T * cap;   // (work items / flagged candidates of this range's slots)
+            q.wq_n = k_counters; q.fq_n = k_counters + K1S_MAX_SETS;
             q.wq_stride = e->k1_wq_stride;
             q.first_frac = (double)K1S_FIRST_ROUND_FRAC;
             q.spec = 0;
-            const int par = (int)(e->k1_calls & 1ull);
-            e->k1_calls++;
-            q.stats_cur = e->d_k1_stats + 2 * par; q.stats_prev = e->d_k1_stats + 2 * (par ^ 1);
+            const int par = (int)(k_calls & 1ull);
+            k_calls++;
+            q.stats_cur = k_stats + 2 * par; q.stats_prev = k_stats + 2 * (par ^ 1);
             q.dbg = e->d_k1_dbg;
             q.cap = e->k1_cap;
             const long long n_slots = (long long)n * c.n_streams;
@@ -608,7 +656,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                 if (cc <= want_chunk && cc <= K1F_MAX_CHUNK && portion4 % cc == 0) { q.chunk = cc; break; }
             q.n_slots = (int)n_slots;
             q.round = 0; q.select_only = 0; q.gen_only = 0;
-            CU(cudaMemsetAsync(e->d_k1_counters, 0, 2 * K1S_MAX_SETS * sizeof(int), stream));
+            CU(cudaMemsetAsync(k_counters, 0, 2 * K1S_MAX_SETS * sizeof(int), stream));
             CU(cudaMemsetAsync(q.stats_cur, 0, 2 * sizeof(unsigned long long), stream));
             if (q.dbg) CU(cudaMemsetAsync(q.dbg, 0, K1S_MAX_ROUNDS * 4 * sizeof(unsigned long long), stream));
             e->k1_ev_n = 0;
@@ -645,8 +693,8 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             // 1.21 / 1.18, 512 frames 1.78 / 1.69, 1024 frames 2.92 / 2.96)
             const int ov_mode = e->k1_overlap_fixed ? e->k1_overlap : (n_slots <= 768 ? 2 : 1);
             const bool overlap = ov_mode && !e->k1_profile && !fused;
-            cudaStream_t side = overlap ? e->k1_side : stream;
-            cudaStream_t solve_side = (overlap && ov_mode >= 2) ? e->k1_side2 : side;
+            cudaStream_t side = overlap ? k_side : stream;
+            cudaStream_t solve_side = (overlap && ov_mode >= 2) ? k_side2 : side;
             const size_t n_slots_cap = (size_t)e->cfg.max_frames * c.n_streams * (size_t)e->k1_cap;
             mark(-1);
             {
@@ -676,16 +724,16 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                 q.portion = portioned ? (r == 0 ? portion4 : 2 * portion4) : e->k1_cap;   // round 1 may use the whole capacity too
                 q.round_limit = q.portion * sets;
                 const int fgrid = (int)std::min<long long>(e->k1_filter_grid, n_slots * ((q.portion + q.chunk - 1) / q.chunk));
-                if (overlap && r > 0) CU(cudaStreamWaitEvent(stream, e->k1_ev_round, 0));   // the selection needs the previous round's solves
+                if (overlap && r > 0) CU(cudaStreamWaitEvent(stream, k_ev_round, 0));   // the selection needs the previous round's solves
                 if (fused) {
                     // one stream: slot (select + first portion), then per set { filter(k) | generator(k+1) } fused, solve(k)
-                    q.gen_only = 0; q.qidx = set; q.fqidx = set; q.fq = e->d_k1_fq + (size_t)(set & 1) * n_slots_cap;
+                    q.gen_only = 0; q.qidx = set; q.fqidx = set; q.fq = e->d_k1_fq + o * T * cap + (size_t)(set & 1) * n_slots_cap;
                     launch_slot(q);
                     mark(0);
                     e->launches++;
                     for (int k = 0; k < sets && set < K1S_MAX_SETS; k++, set++) {
                         K1SplitParams qf = q;
-                        qf.gen_only = 0; qf.qidx = set; qf.fqidx = set; qf.fq = e->d_k1_fq + (size_t)(set & 1) * n_slots_cap;
+                        qf.gen_only = 0; qf.qidx = set; qf.fqidx = set; qf.fq = e->d_k1_fq + o * T * cap + (size_t)(set & 1) * n_slots_cap;
                         if (k + 1 < sets && set + 1 < K1S_MAX_SETS) {
                             K1SplitParams qg = q;
                             qg.gen_only = 1; qg.qidx = set + 1; qg.fqidx = set + 1;
@@ -710,7 +758,7 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                     q.gen_only = (k > 0);
                     q.qidx = set;
                     q.fqidx = fset;
-                    q.fq = e->d_k1_fq + (size_t)(fset & 1) * (size_t)n_slots_cap;
+                    q.fq = e->d_k1_fq + o * T * cap + (size_t)(fset & 1) * (size_t)n_slots_cap;
                     if (use_spec && r == 0 && k == 0) {
                         K1SpecParams spp;
                         spp.vstate = e->d_k1_vstate; spp.vcells = e->d_k1_vcells; spp.vendw = e->d_k1_vendw; spp.result = e->d_k1_spec_result; spp.table = e->d_k1_spec_table;
@@ -723,27 +771,27 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                     }
                     mark(0);
                     if (overlap) {
-                        CU(cudaEventRecord(e->k1_ev_gen[set], stream));
-                        CU(cudaStreamWaitEvent(side, e->k1_ev_gen[set], 0));
-                        if (!batch && solve_side != side && set >= 2) CU(cudaStreamWaitEvent(side, e->k1_ev_solve[set - 2], 0));   // the flag-queue region is free again
+                        CU(cudaEventRecord(k_ev_gen[set], stream));
+                        CU(cudaStreamWaitEvent(side, k_ev_gen[set], 0));
+                        if (!batch && solve_side != side && set >= 2) CU(cudaStreamWaitEvent(side, k_ev_solve[set - 2], 0));   // the flag-queue region is free again
                     }
                     k1_filter<<<fgrid, K1F_THREADS, sizeof(K1FSmem), side>>>(q);
                     if (!overlap) mark(1);
                     e->launches += 2;
                     if (!solve_now) continue;
                     if (solve_side != side) {
-                        CU(cudaEventRecord(e->k1_ev_filt[set], side));
-                        CU(cudaStreamWaitEvent(solve_side, e->k1_ev_filt[set], 0));
+                        CU(cudaEventRecord(k_ev_filt[set], side));
+                        CU(cudaStreamWaitEvent(solve_side, k_ev_filt[set], 0));
                     }
                     if (few && e->k1_solve_group4) k1_solve4<<<e->k1_solve_grid, K1V_THREADS, 0, solve_side>>>(q);
                     else k1_solve<<<e->k1_solve_grid, K1V_THREADS, 0, solve_side>>>(q);
-                    if (solve_side != side) CU(cudaEventRecord(e->k1_ev_solve[set], solve_side));
+                    if (solve_side != side) CU(cudaEventRecord(k_ev_solve[set], solve_side));
                     if (!overlap) mark(2);
                     e->launches++;
                 }
-                if (overlap) CU(cudaEventRecord(e->k1_ev_round, solve_side));
+                if (overlap) CU(cudaEventRecord(k_ev_round, solve_side));
             }
-            if (overlap) CU(cudaStreamWaitEvent(stream, e->k1_ev_round, 0));
+            if (overlap) CU(cudaStreamWaitEvent(stream, k_ev_round, 0));
             q.round = n_rounds; q.select_only = 1; q.gen_only = 0;
             launch_slot(q);
             mark(0);
@@ -820,6 +868,25 @@ static int forward_split(dsac_engine* e, int32_t n, int64_t frame0, const int16_
     if (allow_split && e->tail_split && !e->k1_mode && (e->stages & DSAC_STAGE_SAMPLE) && (e->stages & ~DSAC_STAGE_SAMPLE) && !e->hook) {
         const int per_wave = e->k1_slots / std::max(1, e->cfg.n_streams);   // frames per sampler wave
         if (per_wave >= 1 && n > per_wave && n % per_wave != 0) n1 = (n / per_wave) * per_wave;
+    }
+    // Two lanes (split sampler): a large batch as two concurrent half-batches, each a complete pass (sampler, H x N matrix,
+    // refinement) over its frames with its own queues, counters and side streams.  The passes de-phase on the GPU -- one half's
+    // generator and latency-bound refinement run beside the other half's register-filling filter -- which a single pass,
+    // whose kernels depend on each other in sequence, cannot: 2.90 -> 2.69 ms per 1024 frames; three or more lanes are slower
+    // (3.10 / 3.31 ms: tools/lane_probe.py).  Frames are independent and sampler streams keyed by the global frame index, so
+    // results do not depend on the split.
+    if (allow_split && e->k1_mode && e->k1_lanes && n >= 768 && e->lane1.main && !e->k1_profile && !e->d_k1_dbg && !e->k1_fused &&
+        !e->hook && (e->stages & DSAC_STAGE_SAMPLE)) {
+        const int32_t na = n / 2;
+        const size_t N = DSAC_N, f = (size_t)na;
+        CU(cudaEventRecord(e->ev_fork, stream));
+        CU(cudaStreamWaitEvent(e->lane1.main, e->ev_fork, 0));
+        int rc = forward_range(e, na, n - na, frame0 + na, d_coords + f * N * 3, pix_shared ? d_pix : d_pix + f * N * 2, pix_shared,
+                               d_gt_jp ? d_gt_jp + f * 12 : nullptr, e->lane1.main, 1);
+        cudaEventRecord(e->ev_join, e->lane1.main);   // the caller's stream joins the lane again whatever happens below
+        if (rc == DSAC_OK) rc = forward_range(e, 0, na, frame0, d_coords, d_pix, pix_shared, d_gt_jp, stream, 0);
+        CU(cudaStreamWaitEvent(stream, e->ev_join, 0));
+        return rc;
     }
     if (n1 <= 0) return forward_range(e, 0, n, frame0, d_coords, d_pix, pix_shared, d_gt_jp, stream);
     const size_t N = DSAC_N, f = (size_t)n1;
