@@ -877,7 +877,8 @@ static int forward_split(dsac_engine* e, int32_t n, int64_t frame0, const int16_
     // results do not depend on the split.
     if (allow_split && e->k1_mode && e->k1_lanes && n >= 768 && e->lane1.main && !e->k1_profile && !e->d_k1_dbg && !e->k1_fused &&
         !e->hook && (e->stages & DSAC_STAGE_SAMPLE)) {
-        const int32_t na = n / 2;
+        int32_t na = n / 2;
+        if (const char* lf = getenv("DSAC_K1_LANE_FRAC")) na = std::max(1, std::min(n - 1, (int32_t)(atof(lf) * n)));   // development aid
         const size_t N = DSAC_N, f = (size_t)na;
         CU(cudaEventRecord(e->ev_fork, stream));
         CU(cudaStreamWaitEvent(e->lane1.main, e->ev_fork, 0));
