@@ -648,7 +648,8 @@ def main():
                        "noise_mm": 25.0, "data_seed": 20170721, "sampler_seed": 1305, "alpha": 0.1, "beta": 0.5,
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                        "sampler": "round-based pipeline of flat kernels (sampler_split.cuh), %d launches per pass" % (gpu_launches // max(1, args.steps)),
-                       "l2": "256 MB buffer written between timed steps (flush); each step also streams %.2f GB of diffmaps" % (BYTES_M * nf / 1e9)},
+                       "l2": "256 MB buffer written between timed steps (flush); each step also streams %.2f GB of diffmaps" % (BYTES_M * nf / 1e9),
+                       "schedule": "one step = one dsac_forward_device call; inside it a batch of >= 768 frames runs as two concurrent half-batches (lanes: own queues, counters, side streams; bit-identical results), DESIGN.md section 9"},
             "e2e": {"value": e2e_value, "unit": "hyp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(t[0].item()) / args.steps,
                     "api": "dsac_forward_submit / dsac_forward_wait, three engines in flight on the GPU (the driver's frame loop): every step "
