@@ -270,4 +270,16 @@ extern "C" void shim_mt_twist3(uint32_t seed, int n_blocks, uint32_t* out) {
 }
 
 // k_sample's pair-based candidate parser (windows without rejected draws) against the reference loop on the same pairs
+// `count` consecutive candidates parsed from pair `sp` on (cand_pairs_len, the generator's own routine): end pair of each;
+// returns the number parsed before the window ran out
+extern "C" int shim_parse_run(const unsigned short* pr16, int sp, int limit, int count, int* end_pair) {
+    int n = 0;
+    while (n < count) {
+        const int len = dsac::cand_pairs_len(pr16, sp, limit);
+        if (len < 0) break;
+        sp += len;
+        end_pair[n++] = sp;
+    }
+    return n;
+}
 extern "C" int shim_cand_pairs_len(const unsigned short* pr16, int sp, int limit) { return dsac::cand_pairs_len(pr16, sp, limit); }
