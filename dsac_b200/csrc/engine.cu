@@ -142,6 +142,10 @@ struct dsac_engine {
     uint32_t* d_k1_vendw = nullptr;
     int* d_k1_spec_result = nullptr;
     int* d_k1_spec_table = nullptr;
+    uint32_t* d_k1_chain = nullptr;               // k1_pipe: hand-over records of the window chain, [slots][K1Q_MAX_WIN + 1][4]
+    unsigned long long k1_epoch = 0;              // k1_pipe: one value per launch, engine-wide (a stale hand-over record never matches)
+    int k1_pipe = 0;                              // DSAC_K1_PIPE=1: chained generator for 9 .. ~190 streams (experimental, off by default)
+    int k1_slot_capacity = 0;                     // CTAs of k1_pipe / k1_slot (256 threads) the GPU holds at once
     int k1_spec_slots = 0;                        // streams the scratch above was sized for (0: speculative round off)
     int k1_solve_group4 = 1;                      // DSAC_K1_SOLVE4: four lanes per flagged candidate for a few streams
     int k1_slot_threads = 0;                      // DSAC_K1_SLOT_THREADS: 256 / 512 / 1024 (0: by the number of streams)
@@ -254,7 +258,7 @@ void dsac_engine_destroy(dsac_engine* e) {
         if (L.counters) cudaFree(L.counters);
         if (L.stats) cudaFree(L.stats);
     }
-    void* k1ptrs[] = {e->d_k1_spec_table, e->d_k1_vstate, e->d_k1_vcells, e->d_k1_vendw, e->d_k1_spec_result, e->d_k1_state, e->d_k1_celltab, e->d_k1_cells, e->d_k1_endw, e->d_k1_accbits, e->d_k1_pose, e->d_k1_wq,
+    void* k1ptrs[] = {e->d_k1_chain, e->d_k1_spec_table, e->d_k1_vstate, e->d_k1_vcells, e->d_k1_vendw, e->d_k1_spec_result, e->d_k1_state, e->d_k1_celltab, e->d_k1_cells, e->d_k1_endw, e->d_k1_accbits, e->d_k1_pose, e->d_k1_wq,
                       e->d_k1_fq, e->d_k1_counters, e->d_k1_stats, e->d_k1_dbg};
     for (void* p : k1ptrs)
         if (p) cudaFree(p);
@@ -396,6 +400,14 @@ int dsac_engine_create(const dsac_config* cfg, dsac_engine** out) {
         CUC(cudaMalloc(&e->d_k1_wq, (size_t)K1S_MAX_SETS * slots * 128 * sizeof(uint2)));
         CUC(cudaMalloc(&e->d_k1_fq, 2 * slots * cap * sizeof(uint32_t)));   // two regions: the filter of set k+1 writes one while the solve of set k reads the other
         CUC(cudaMalloc(&e->d_k1_counters, 2 * K1S_MAX_SETS * sizeof(int)));
+        CUC(cudaMalloc(&e->d_k1_chain, slots * (K1Q_MAX_WIN + 1) * 4 * sizeof(uint32_t)));
+        CUC(cudaMemset(e->d_k1_chain, 0, slots * (K1Q_MAX_WIN + 1) * 4 * sizeof(uint32_t)));
+        {
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_pipe, K1S_THREADS, 0);
+            e->k1_slot_capacity = std::max(1, per_sm) * e->sm_count;
+            if (const char* pv = getenv("DSAC_K1_PIPE")) e->k1_pipe = atoi(pv);
+        }
         {   // speculative first round for a few streams (sampler_split.cuh: k1_spec / k1_stitch); DSAC_K1_SPEC=0 turns it off
             int want = 1;
             if (const char* sv = getenv("DSAC_K1_SPEC")) want = atoi(sv);
@@ -714,11 +726,15 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
             // stream's first round is several windows long (>= 64 hypotheses per stream) and the GPU is otherwise idle
             const int quota_max = (c.n_hyps + c.n_streams - 1) / c.n_streams;
             const bool use_spec = few && off == 0 && n_slots <= e->k1_spec_slots && quota_max >= 64 && c.max_candidates >= (1 << 16) && !fused_req;   // (the candidate bound cannot fall inside the speculative round)
+            // chained generator (k1_pipe): K CTAs per stream, all of them resident at once
+            const int pipe_K = (int)std::min<long long>(8, e->k1_slot_capacity / std::max<long long>(1, n_slots));
+            const bool use_pipe = e->k1_pipe && !use_spec && pipe_K >= 3 && n_slots >= 9 && quota_max >= 64 && c.max_candidates >= (1 << 16) &&
+                                  !fused_req && !e->k1_profile;
             const int n_rounds = (few && !e->k1_rounds_fixed) ? std::min(e->k1_rounds, 2) : e->k1_rounds;
             for (int r = 0; r < n_rounds; r++) {
                 // portions only pay when the generator has the whole GPU to fill (many streams); a few streams (single-frame
                 // latency, BASELINE config 2) take every round in one launch set: fewer dependent launches
-                const bool portioned = (n_slots >= 128 || port_forced) && r < 2 && n_port > 1;
+                const bool portioned = (n_slots >= 128 || port_forced) && r < 2 && n_port > 1 && !(use_pipe && r == 0);
                 const int sets = portioned ? (r == 0 ? n_port : n_port / 2) : 1;
                 q.round = r;
                 q.portion = portioned ? (r == 0 ? portion4 : 2 * portion4) : e->k1_cap;   // round 1 may use the whole capacity too
@@ -766,6 +782,12 @@ static int forward_range(dsac_engine* e, int32_t off, int32_t n, int64_t frame0,
                         k1_stitch<<<(unsigned)n_slots, K1T_THREADS, 0, stream>>>(q, spp);
                         k1_gather<<<dim3((unsigned)((e->k1_cap + K1G_PER_CTA - 1) / K1G_PER_CTA), (unsigned)n_slots), K1G_THREADS, 0, stream>>>(q, spp);
                         e->launches += 2;
+                    } else if (use_pipe && r == 0 && k == 0) {
+                        K1PipeParams ppm;
+                        ppm.chain = e->d_k1_chain + o * T * (K1Q_MAX_WIN + 1) * 4;
+                        ppm.epoch = (uint32_t)(++e->k1_epoch & 0x7fffffffull) + 1u;
+                        ppm.K = pipe_K;
+                        k1_pipe<<<dim3((unsigned)pipe_K, (unsigned)n_slots), K1S_THREADS, 0, stream>>>(q, ppm);
                     } else {
                         launch_slot(q);
                     }

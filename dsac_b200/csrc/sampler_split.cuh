@@ -916,6 +916,283 @@ __global__ void __launch_bounds__(K1G_THREADS) k1_gather(K1SplitParams q, K1Spec
     }
 }
 
+// ------------------------------------------------------------------ k1_pipe: one stream generated by K CTAs in a chain
+// For 9 .. ~190 streams (strong scaling: 128 frames per GPU) the four-fold windows of k1_spec do not fit the GPU, but a stream's
+// first round is still one CTA's serial chain.  Here K CTAs share a stream: window w (K1P_W stream words) belongs to CTA w mod K.
+// Every CTA twists through ALL state blocks (without decoding those of the other CTAs' windows: the cheap part) and decodes,
+// scans, parses and writes only its own windows.  The one thing a window needs from its predecessor -- the stream position of its
+// first candidate and the number of candidates before it -- is published by the predecessor right after its walk and awaited by
+// a spin on a global flag; a stream's CTAs have consecutive block indices in window order, so the CTA that is waited for is
+// always dispatched first.  No speculation, nothing to stitch: every candidate is written at its final index.  Any irregularity
+// (a rejected Lemire draw, an event-list overflow, a candidate that does not fit its window's margin) aborts the chain: the
+// stream is left at its seeded state and the next, ordinary round generates it.
+constexpr int K1Q_MARGIN = 256;                           // stream words decoded beyond a window (the straddling candidate)
+constexpr int K1Q_MAX_WIN = 32;
+struct K1PipeParams {
+    uint32_t* chain;      // [slots][K1Q_MAX_WIN + 1][4]: stream position, candidates before, abort, flag (== epoch when valid)
+    uint32_t epoch;       // > 0, different for every call of an engine lane
+    int K;                // CTAs per stream
+};
+
+__device__ __forceinline__ int k1_pipe_windows(const K1SplitParams& q, int quota) {
+    double prior = 0;
+    if (q.stats_prev && q.stats_prev[1] > 0) prior = (double)q.stats_prev[0] / (double)q.stats_prev[1];
+    const double n = q.first_frac * ((prior > 0) ? prior : 64.0) * quota;
+    int nw = (int)(n / (K1P_W / 8) + 0.5);
+    if (nw > K1Q_MAX_WIN) nw = K1Q_MAX_WIN;
+    while (nw > 0 && (long long)nw * (K1P_W / 8 + 8) > (long long)q.cap) nw--;
+    return nw < 2 ? 0 : nw;
+}
+
+__global__ void __launch_bounds__(K1S_THREADS, K1S_MIN_BLOCKS) k1_pipe(K1SplitParams q, K1PipeParams pp) {
+    __shared__ K1GSmem sm;
+    __shared__ uint32_t s_P, s_base, s_abort, s_count, s_pnext;
+    const SampleParams& p = q.sp;
+    const int tid = threadIdx.x, lane = tid & 31, warp_id = tid >> 5;
+    const int kk = blockIdx.x, slot = blockIdx.y;
+    const int frame = slot / p.T, s = slot - frame * p.T;
+    int h0, quota;
+    stream_chunk(p.H, p.T, s, &h0, &quota);
+    K1SlotState& S = q.state[slot];
+    const uint32_t pos0 = (s == 0) ? p.skip : 0u;
+    if (quota == 0) {
+        if (kk == 0 && tid == 0) {
+            S.done = 1; S.acc = 0; S.n_round = 0; S.target = 0; S.cand_base = 0; S.left_n = 0; S.any_reject = 0; S.overflow = 0; S.pos = 0; S.gen = 0;
+            p.stream_ncand[slot] = 0;
+            p.stream_endpos[slot] = 0;
+        }
+        return;
+    }
+    const int n_win = k1_pipe_windows(q, quota);
+    if (n_win == 0) {      // not worth it (few hypotheses per stream): the ordinary round generates the stream
+        if (kk == 0 && tid == 0) {
+            S.pos = pos0; S.gen = 0; S.acc = 0; S.cand_base = 0; S.n_round = 0; S.target = 0; S.done = 0; S.left_n = 0; S.any_reject = 0; S.overflow = 0;
+        }
+        return;
+    }
+    volatile uint32_t* chain = pp.chain + (size_t)slot * (K1Q_MAX_WIN + 1) * 4;
+    const size_t cbase = (size_t)slot * q.cap;
+    // the seeded state (k1_cells); cur_block = regenerations done = first stream word of the next block / 624
+    for (int k = tid; k < MT_N; k += K1S_THREADS) sm.st[k] = S.mt[k];
+    __syncthreads();
+    uint32_t par = 0;
+    uint32_t own[3] = {0u, 0u, 0u};
+    if (tid < K1_WAVE) {
+        own[0] = sm.st[tid]; own[1] = sm.st[tid + K1_WAVE];
+        if (tid + 2 * K1_WAVE < MT_N) own[2] = sm.st[tid + 2 * K1_WAVE];
+    }
+    uint32_t cur_block = 0;
+    constexpr int SCAN_END = (K1P_W + K1Q_MARGIN) / 2;        // pairs scanned per window
+    constexpr int L_PAIRS = K1P_W / 2;                         // a candidate belongs to the window its first pair lies in
+    for (int w = kk; w < n_win; w += pp.K) {
+        const uint32_t O = pos0 + (uint32_t)w * (uint32_t)K1P_W;
+        if (tid == 0) sm.any_reject = 0;
+        __syncthreads();
+        // ---- twist to the window (no decode), then twist + decode the words [O, O + W + margin)
+        while ((cur_block + 1u) * (uint32_t)MT_N <= O || cur_block * (uint32_t)MT_N < O + (uint32_t)(K1P_W + K1Q_MARGIN)) {
+            const bool decode = (cur_block + 1u) * (uint32_t)MT_N > O;
+            const uint32_t* so = sm.st + par * MT_N;
+            uint32_t* sn = sm.st + (par ^ 1u) * MT_N;
+            if (tid < K1_WAVE) {
+                uint32_t x[3];
+                mt_twist3(so, tid, own, x);
+                own[0] = x[0]; own[1] = x[1]; own[2] = x[2];
+                const bool has3 = tid + 2 * K1_WAVE < MT_N;
+                bool rej_any = false;
+#pragma unroll
+                for (int ww = 0; ww < 3; ww++) {
+                    if (ww < 2 || has3) {
+                        const int k = tid + ww * K1_WAVE;
+                        sn[k] = x[ww];
+                        if (decode) {
+                            const uint32_t tv = mt_temper(x[ww]);
+                            const uint32_t hi = __umulhi(tv, (uint32_t)DSAC_GRID_CONST), lo = tv * (uint32_t)DSAC_GRID_CONST;
+                            const bool rej = lo < ((0u - DSAC_GRID_CONST) % DSAC_GRID_CONST);
+                            const int off = (int)(cur_block * (uint32_t)MT_N + (uint32_t)k - O);   // stream word O + off
+                            if (off >= 0 && off < K1S_WORDS) {
+                                sm.vals[off] = rej ? (unsigned char)255 : (unsigned char)hi;
+                                rej_any |= rej;
+                            }
+                        }
+                    }
+                }
+                if (rej_any) sm.any_reject = 1;
+            }
+            par ^= 1u;
+            cur_block++;
+            __syncthreads();
+        }
+        const int w_avail = min((int)(cur_block * (uint32_t)MT_N - O), K1S_WORDS);   // decoded words from O on (>= W + margin)
+        // ---- scan for repeated pairs (as k1_slot_body)
+        const unsigned short* pr16 = reinterpret_cast<const unsigned short*>(sm.vals);
+        {
+            const uint4* v128 = reinterpret_cast<const uint4*>(sm.vals);
+            constexpr int n_blocks = (SCAN_END + 7) >> 3;
+            constexpr int NWS = K1S_WARPS < 8 ? K1S_WARPS : 8;
+            constexpr int bseg = ((n_blocks + NWS - 1) / NWS + 31) & ~31;
+            const int bbeg = min(warp_id * bseg, n_blocks), bend = (warp_id < NWS) ? min(bbeg + bseg, n_blocks) : bbeg;
+            int cnt = 0;
+            for (int b0 = bbeg; b0 < bend; b0 += 32) {
+                const int b = b0 + lane;
+                uint32_t wv[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                if (b < bend) {
+                    const uint4 cur = v128[b];
+                    wv[2] = cur.x; wv[3] = cur.y; wv[4] = cur.z; wv[5] = cur.w;
+                    if (b > 0) {
+                        const uint2 prv = *reinterpret_cast<const uint2*>(sm.vals + 16 * b - 8);
+                        wv[0] = prv.x; wv[1] = prv.y;
+                    }
+                }
+                uint32_t any = 0;
+#pragma unroll
+                for (int j2 = 2; j2 < 6; j2++) {
+                    const uint32_t s1 = __funnelshift_l(wv[j2 - 1], wv[j2], 16);
+                    const uint32_t s3 = __funnelshift_l(wv[j2 - 2], wv[j2 - 1], 16);
+                    const uint32_t x1 = wv[j2] ^ s1, x2 = wv[j2] ^ wv[j2 - 1], x3 = wv[j2] ^ s3;
+                    any |= ((x1 - 0x00010001u) & ~x1) | ((x2 - 0x00010001u) & ~x2) | ((x3 - 0x00010001u) & ~x3);
+                }
+                const bool has = (b < bend) && (any & 0x80008000u) != 0u;
+                if (__any_sync(0xffffffffu, has)) {
+                    uint32_t evs[8];
+                    int ne = 0;
+                    if (has) {
+#pragma unroll
+                        for (int h2 = 0; h2 < 8; h2++) {
+                            const int k = 8 * b + h2;
+                            const uint32_t wj = wv[2 + (h2 >> 1)], wp1 = wv[1 + (h2 >> 1)], wp2 = wv[(h2 >> 1)];
+                            uint32_t pk, q1, q2, q3;
+                            if (h2 & 1) { pk = wj >> 16; q1 = wj & 0xffffu; q2 = wp1 >> 16; q3 = wp1 & 0xffffu; }
+                            else { pk = wj & 0xffffu; q1 = wp1 >> 16; q2 = wp1 & 0xffffu; q3 = wp2 >> 16; }
+                            const uint32_t d = (pk == q1) ? 1u : (pk == q2) ? 2u : (pk == q3) ? 3u : 0u;
+                            if (d && k < SCAN_END) evs[ne++] = ((uint32_t)k << 2) | d;
+                        }
+                    }
+                    int incl = ne;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (lane >= off) incl += o;
+                    }
+                    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                    const int at = cnt + incl - ne;
+                    for (int e = 0; e < ne; e++)
+                        if (at + e < K1_EV_CAP) sm.ev[warp_id][at + e] = evs[e];
+                    cnt += tot;
+                }
+            }
+            if (lane == 0 && warp_id < NWS) sm.ev_n[warp_id] = cnt;
+        }
+        __syncthreads();
+        // ---- the predecessor's hand-over, the walk from there, the hand-over to the successor
+        if (tid == 0) {
+            uint32_t P = pos0, base = 0u, abort_ = sm.any_reject ? 1u : 0u;
+            if (w > 0) {
+                while (chain[w * 4 + 3] != pp.epoch) __nanosleep(40);
+                __threadfence();
+                P = chain[w * 4 + 0]; base = chain[w * 4 + 1]; abort_ |= chain[w * 4 + 2];
+            }
+            int cur = (int)(P - O) >> 1, ci = 0, nb = 1, stop_at = -1;
+            if (P < O || ((P - O) & 1u) || cur >= 64) abort_ = 1u;
+            uint32_t count = 0u, pnext = 0u;
+            if (!abort_) {
+                constexpr int NWS = K1S_WARPS < 8 ? K1S_WARPS : 8;
+                bool fail = false;
+                sm.brk_ci[0] = 0; sm.brk_cur[0] = (unsigned short)cur;
+                for (int wi = 0; wi < NWS && !fail && stop_at < 0; wi++) {
+                    const int n = sm.ev_n[wi];
+                    if (n > K1_EV_CAP) { fail = true; break; }
+                    for (int e = 0; e < n; e++) {
+                        const uint32_t evv = sm.ev[wi][e];
+                        const int k = (int)(evv >> 2), d = (int)(evv & 3u);
+                        if (k < cur) continue;
+                        const int j = (k - cur) >> 2, spp = cur + 4 * j;
+                        if (k - d < spp) continue;
+                        if (spp >= L_PAIRS + 32) { stop_at = ci + j; break; }   // far enough into the margin
+                        const int np = cand_pairs_len(pr16, spp, SCAN_END);
+                        if (np < 0) { stop_at = ci + j; break; }
+                        if (nb >= K1_BRK_CAP) { fail = true; break; }
+                        ci += j + 1;
+                        cur = spp + np;
+                        sm.brk_ci[nb] = (unsigned short)ci;
+                        sm.brk_cur[nb] = (unsigned short)cur;
+                        nb++;
+                    }
+                }
+                int n_ok = ci + ((SCAN_END - cur) >> 2);       // clean 4-pair candidates after the last break
+                if (stop_at >= 0) n_ok = min(n_ok, stop_at);
+                if (fail) abort_ = 1u;
+                else {
+                    // candidates that START before pair L_PAIRS: in the last break segment that begins before L_PAIRS
+                    int m = 0;
+                    while (m + 1 < nb && (int)sm.brk_cur[m + 1] < L_PAIRS) m++;
+                    int cnt = (int)sm.brk_ci[m] + ((L_PAIRS - (int)sm.brk_cur[m] + 3) >> 2);
+                    int start_pair;
+                    if (m + 1 < nb && cnt >= (int)sm.brk_ci[m + 1]) { cnt = (int)sm.brk_ci[m + 1]; start_pair = (int)sm.brk_cur[m + 1]; }
+                    else start_pair = (int)sm.brk_cur[m] + 4 * (cnt - (int)sm.brk_ci[m]);
+                    if (cnt > n_ok || cnt < 1 || start_pair > SCAN_END - 8 || (long long)base + cnt > (long long)q.cap) abort_ = 1u;
+                    count = (uint32_t)cnt;
+                    pnext = O + 2u * (uint32_t)start_pair;
+                    sm.brk_n = nb;
+                }
+            }
+            if (abort_) { count = 0u; pnext = P; }
+            // hand over to window w + 1 (the entry after the last window is the round's result, read below by the last CTA itself)
+            chain[(w + 1) * 4 + 0] = pnext; chain[(w + 1) * 4 + 1] = base + count; chain[(w + 1) * 4 + 2] = abort_;
+            __threadfence();
+            chain[(w + 1) * 4 + 3] = pp.epoch;
+            s_P = P; s_base = base; s_abort = abort_; s_count = count; s_pnext = pnext;
+        }
+        __syncthreads();
+        const uint32_t base = s_base, count = s_count;
+        if (!s_abort) {
+            // ---- start offsets and the candidates themselves, at their final index
+            const int nb = sm.brk_n;
+            int m = 0;
+            for (int i = tid; i <= (int)count; i += K1S_THREADS) {
+                while (m + 1 < nb && (int)sm.brk_ci[m + 1] <= i) m++;
+                sm.cand_start[i] = (unsigned short)(2 * ((int)sm.brk_cur[m] + 4 * (i - (int)sm.brk_ci[m])));
+            }
+            __syncthreads();
+            for (int i = tid; i < (int)count; i += K1S_THREADS) {
+                int cells[4];
+                cand_parse_fast(sm.vals, sm.cand_start[i], w_avail, cells);
+                q.cells[cbase + base + i] = make_uint2((uint32_t)cells[0] | ((uint32_t)cells[1] << 16), (uint32_t)cells[2] | ((uint32_t)cells[3] << 16));
+                q.endw[cbase + base + i] = O + (uint32_t)sm.cand_start[i + 1];
+            }
+        }
+        if (w == n_win - 1) {
+            // ---- the last window closes the round: state, accept bits, work items (or the fresh state if the chain aborted)
+            const int n_total = s_abort ? 0 : (int)(base + count);
+            if (s_abort) {
+                if (tid == 0) {
+                    S.pos = pos0; S.gen = 0; S.acc = 0; S.cand_base = 0; S.n_round = 0; S.target = 0; S.done = 0; S.left_n = 0;
+                    S.any_reject = 0; S.overflow = 0;
+                }
+            } else {
+                const uint32_t P_end = s_pnext, gen = cur_block * (uint32_t)MT_N;
+                const int left = min((int)(gen - P_end), K1S_LEFT_CAP), left_off = (int)(P_end - O);
+                const uint32_t* half = sm.st + par * MT_N;
+                for (int k = tid; k < MT_N; k += K1S_THREADS) S.mt[k] = half[k];
+                for (int k = tid; k < left; k += K1S_THREADS) S.left[k] = sm.vals[left_off + k];
+                uint32_t* ab = q.accbits + (size_t)slot * (q.cap >> 5);
+                for (int k = tid; k < ((n_total + 31) >> 5); k += K1S_THREADS) ab[k] = 0u;
+                const int n_items = (n_total + q.chunk - 1) / q.chunk;
+                if (tid == 0) s_P = (uint32_t)atomicAdd(q.wq_n + q.qidx, n_items);
+                __syncthreads();
+                uint2* wq = q.wq + (size_t)q.qidx * q.wq_stride + s_P;
+                for (int c = tid; c < n_items; c += K1S_THREADS)
+                    wq[c] = make_uint2((uint32_t)slot * 128u + (uint32_t)c, (uint32_t)min(q.chunk, n_total - c * q.chunk));
+                if (tid == 0) {
+                    S.pos = P_end; S.gen = gen; S.acc = 0; S.cand_base = 0; S.n_round = n_total; S.target = n_total; S.done = 0;
+                    S.left_n = left; S.any_reject = 0; S.overflow = (int)(gen - P_end) > K1S_LEFT_CAP ? 1 : 0;
+                    if (q.dbg) { atomicAdd(q.dbg + 0, 1ull); atomicAdd(q.dbg + 1, (unsigned long long)n_total); }
+                }
+            }
+        }
+        __syncthreads();      // vals / event lists are reused by this CTA's next window
+    }
+}
+
 // ------------------------------------------------------------------ k1_filter
 // The filter's inputs straight from the cell table: bearings of points 0..2 from the stored 1/|(u, v, 1)|.
 __device__ __forceinline__ bool k1_filter_candidate(const CellRec* cell, const int cells[4], double f, double cx, double cy,

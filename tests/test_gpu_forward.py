@@ -85,6 +85,28 @@ def test_speculative_first_round_is_scheduling_only(engine_mod, oracle, T, nf, m
         assert fw.n_candidates == a.n_candidates[f]
 
 
+@pytest.mark.parametrize("T,nf", [(1, 12), (2, 20), (1, 150)])
+def test_chained_generator_is_scheduling_only(engine_mod, oracle, T, nf, monkeypatch):
+    """k1_pipe (DSAC_K1_PIPE=1: K CTAs per stream, window w on CTA w mod K, the first candidate's position handed from window to
+    window through a spin on a global flag) must give exactly the candidates of the one-CTA-per-stream generator and the oracle's."""
+    E, O = engine_mod, oracle
+    H = 256
+    coords, pix, gt_cv, gt_jp = E.synth_frames(nf, n_streams=T)
+    out = {}
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("DSAC_K1_PIPE", pipe)
+        eng = E.Engine(max_frames=nf, n_streams=T, n_hyps=H)
+        out[pipe] = eng.forward(coords, pix, gt_jp)
+        eng.close()
+    a, b = out["1"], out["0"]
+    for name in ("img_idx", "cand_idx", "n_candidates", "hyp_pose", "scores", "ref_pose", "inlier_map", "status"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    for f in (0, nf - 1):
+        fw = _oracle_frame(O, dict(n_hyps=H), coords[f], pix[f], gt_jp[f], f, T)
+        assert np.array_equal(fw.img_idx, a.img_idx[f]) and np.array_equal(fw.cand_idx, a.cand_idx[f])
+        assert fw.n_candidates == a.n_candidates[f]
+
+
 @pytest.mark.parametrize("threads", [256, 512, 1024])
 def test_generator_thread_counts_sample_the_same_sets(engine_mod, oracle, threads, monkeypatch):
     """k1_slot is instantiated for 256 / 512 / 1024 threads per (frame, stream) and chosen by the number of streams
